@@ -1,0 +1,456 @@
+// bpg.cu -- libbpg: context, resident generators, MSM driver and the C ABI (include/bpg.h).
+// Single translation unit: device kernels live in kernels_*.cuh, host protocol code in host_*.h / prover.inl.
+#include "bpg_internal.h"
+#include "consts.h"
+#include "host_merlin.h"
+#include "kernels_core.cuh"
+#include "kernels_msm.cuh"
+#include "kernels_vec.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <thread>
+
+static thread_local std::string g_cuda_err;
+void bpg_set_cuda_error(cudaError_t e, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s:%d: %s (%s)", file, line, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_cuda_err = buf;
+}
+#define CTX_TRY(x) do { int rc_ = (x); if (rc_ != BPG_OK) { if (rc_ == BPG_E_CUDA) ctx->last_error = g_cuda_err; return rc_; } } while (0)
+#define KCHECK() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { bpg_set_cuda_error(e_, __FILE__, __LINE__); ctx->last_error = g_cuda_err; return BPG_E_CUDA; } } while (0)
+
+int dev_buf::ensure(size_t bytes) {
+    if (bytes <= cap) return BPG_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return BPG_OK;
+}
+void dev_buf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+static int ensure_pinned(bpg_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->h_pinned_cap) return BPG_OK;
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0;
+    CUDA_TRY(cudaMallocHost(&ctx->h_pinned, bytes + 4096));
+    ctx->h_pinned_cap = bytes + 4096;
+    return BPG_OK;
+}
+
+// ================================================================ context
+extern "C" const char *bpg_strerror(int code) {
+    switch (code) {
+    case BPG_OK: return "ok";
+    case BPG_E_CUDA: return "CUDA error";
+    case BPG_E_SIZE: return "invalid size / generator capacity";
+    case BPG_E_DECOMPRESS: return "point decompression failed";
+    case BPG_E_ARG: return "invalid argument";
+    case BPG_E_FORMAT: return "proof format error";
+    case BPG_E_NOMEM: return "out of memory";
+    }
+    return "unknown";
+}
+extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
+    if (!out) return BPG_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(device));
+    if (bpg_init_constants_host() != 0) return BPG_E_ARG;
+    CUDA_TRY(cudaMemcpyToSymbol(c_K, &h_K, sizeof(bpg_consts)));
+    bpg_ctx *ctx = new bpg_ctx();
+    ctx->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+    *out = ctx;
+    return BPG_OK;
+}
+extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->tab) cudaFree(ctx->tab);
+    if (ctx->comb) cudaFree(ctx->comb);
+    dev_buf *bufs[] = {&ctx->counts, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->partial, &ctx->buckets, &ctx->lvlP, &ctx->lvlQ, &ctx->heavy, &ctx->results};
+    for (dev_buf *b : bufs) b->release();
+    for (dev_buf &b : ctx->scratch) b.release();
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+extern "C" const char *bpg_last_error(bpg_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_cuda_err.c_str(); }
+extern "C" uint64_t bpg_launch_count(bpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int bpg_sync(bpg_ctx *ctx) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return BPG_OK; }
+
+extern "C" int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr) { if (!ctx || !d_ptr) return BPG_E_ARG; CUDA_TRY(cudaSetDevice(ctx->device)); CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 1)); return BPG_OK; }
+extern "C" int bpg_dev_free(bpg_ctx *ctx, void *d_ptr) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaFree(d_ptr)); return BPG_OK; }
+extern "C" int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!ctx) return BPG_E_ARG;
+    CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
+extern "C" int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!ctx) return BPG_E_ARG;
+    CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
+
+// ================================================================ generators
+static const uint8_t RISTRETTO_BASEPOINT[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                                0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+
+extern "C" size_t bpg_gens_capacity(bpg_ctx *ctx) { return ctx ? ctx->cap : 0; }
+
+extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
+    if (!ctx) return BPG_E_ARG;
+    if (capacity <= ctx->cap) return BPG_OK;
+    if (capacity > (1u << 22)) return BPG_E_SIZE;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    size_t cap = 64;
+    while (cap < capacity) cap <<= 1;
+    if (ctx->tab) { cudaFree(ctx->tab); ctx->tab = nullptr; }
+    uint32_t ptotal = (uint32_t)(2 * cap + 2);
+    size_t tab_bytes = (size_t)BPG_NWIN * ptotal * sizeof(ge_an);
+    if (cudaMalloc((void **)&ctx->tab, tab_bytes) != cudaSuccess) { cudaGetLastError(); return BPG_E_NOMEM; }
+    if (!ctx->comb) CUDA_TRY(cudaMalloc((void **)&ctx->comb, (size_t)2 * 32 * 128 * sizeof(ge_an)));
+    // SHAKE256 streams on two host threads (sequential squeeze, ~0.3 us per 136 bytes)
+    size_t sbytes = 64 * cap;
+    CTX_TRY(ensure_pinned(ctx, 2 * sbytes + 128));
+    uint8_t *hs = (uint8_t *)ctx->h_pinned;
+    std::thread tg([&] { bpgh::generators_chain_stream('G', 0, hs, cap); });
+    bpgh::generators_chain_stream('H', 0, hs + sbytes, cap);
+    tg.join();
+    // B~ = from_uniform_bytes(SHA3-512(compress(B)))
+    bpgh::sha3_512(hs + 2 * sbytes, RISTRETTO_BASEPOINT, 32);
+    memcpy(hs + 2 * sbytes + 64, RISTRETTO_BASEPOINT, 32);
+    CTX_TRY(ctx->scratch[0].ensure(2 * sbytes + 128));
+    uint8_t *ds = (uint8_t *)ctx->scratch[0].p;
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, 2 * sbytes + 128, cudaMemcpyHostToDevice, ctx->stream));
+    k_gens_tables<<<LAUNCH_1D(2 * cap, 128), 0, ctx->stream>>>(ds, (uint32_t)(2 * cap), 0, ptotal, ctx->tab);
+    KCHECK();
+    CTX_TRY(ctx->scratch[1].ensure(16));
+    uint32_t one = 1;
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch[1].p, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_point_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes + 64, 1, (uint32_t)(2 * cap), ptotal, ctx->tab, (uint32_t *)ctx->scratch[1].p);
+    KCHECK();
+    k_gens_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes, 1, (uint32_t)(2 * cap + 1), ptotal, ctx->tab);
+    KCHECK();
+    k_build_comb<<<1, 64, 0, ctx->stream>>>(ctx->tab, ptotal, (uint32_t)(2 * cap), ctx->comb);
+    KCHECK();
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->cap = cap;
+    ctx->ptotal = ptotal;
+    return BPG_OK;
+}
+
+extern "C" int bpg_gens_export(bpg_ctx *ctx, size_t i0, size_t n, uint8_t *G32, uint8_t *H32) {
+    if (!ctx) return BPG_E_ARG;
+    if (i0 + n > ctx->cap) return BPG_E_SIZE;
+    if (n == 0) return BPG_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->scratch[0].ensure(64 * n));
+    uint8_t *d = (uint8_t *)ctx->scratch[0].p;
+    k_export_kernel<<<LAUNCH_1D(n, 64), 0, ctx->stream>>>(ctx->tab, (uint32_t)i0, (uint32_t)n, d);
+    KCHECK();
+    k_export_kernel<<<LAUNCH_1D(n, 64), 0, ctx->stream>>>(ctx->tab, (uint32_t)(ctx->cap + i0), (uint32_t)n, d + 32 * n);
+    KCHECK();
+    if (G32) CUDA_TRY(cudaMemcpyAsync(G32, d, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (H32) CUDA_TRY(cudaMemcpyAsync(H32, d + 32 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
+extern "C" int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bb32[32]) {
+    if (!ctx || !ctx->cap) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->scratch[0].ensure(64));
+    uint8_t *d = (uint8_t *)ctx->scratch[0].p;
+    k_export_kernel<<<1, 32, 0, ctx->stream>>>(ctx->tab, (uint32_t)(2 * ctx->cap), 2, d);
+    KCHECK();
+    uint8_t h[64];
+    CUDA_TRY(cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (B32) memcpy(B32, h, 32);
+    if (Bb32) memcpy(Bb32, h + 32, 32);
+    return BPG_OK;
+}
+
+// ================================================================ device op wrappers
+static int run_compress(bpg_ctx *ctx, cudaStream_t s, const ge *d_pts, size_t n, uint8_t *d_out32) {
+    if (!n) return BPG_OK;
+    k_compress_kernel<<<LAUNCH_1D(n, 128), 0, s>>>(d_pts, (uint32_t)n, d_out32);
+    KCHECK();
+    return BPG_OK;
+}
+// tree-sum n points into d_out[0] using scratch d_tmp (>= n/64+1 points); d_pts is clobbered when n > 64
+static int run_points_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, size_t n, ge *d_tmp, ge *d_out) {
+    ge *src = d_pts, *dst = d_tmp;
+    while (true) {
+        size_t nb = (n + 63) / 64;
+        ge *o = nb == 1 ? d_out : dst;
+        k_points_sum_kernel<<<(unsigned)nb, 64, 0, s>>>(src, (uint32_t)n, o);
+        KCHECK();
+        if (nb == 1) break;
+        n = nb;
+        ge *t = src; src = dst; dst = t;
+    }
+    return BPG_OK;
+}
+
+int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
+    uint32_t total = 0;
+    for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
+    plan->total = total;
+    int G = plan->ngroups;
+    uint32_t nb = (uint32_t)G * BPG_NBP;
+    size_t maxpairs = (size_t)total * BPG_NWIN;
+    size_t nchunks = (maxpairs + BPG_CHUNK - 1) / BPG_CHUNK + 1;
+    CTX_TRY(ctx->counts.ensure((nb + 2) * 4));
+    CTX_TRY(ctx->offsets.ensure((nb + 2) * 4));
+    CTX_TRY(ctx->cursor.ensure((nb + 2) * 4));
+    CTX_TRY(ctx->sorted.ensure((maxpairs + 1) * 4));
+    CTX_TRY(ctx->partial.ensure(2 * nchunks * sizeof(ge)));
+    CTX_TRY(ctx->buckets.ensure((size_t)nb * sizeof(ge)));
+    CTX_TRY(ctx->heavy.ensure((nb + 2) * 4));
+    size_t lvl = (BPG_NBP + 3) / 4 + 4;
+    CTX_TRY(ctx->lvlP.ensure(2 * (size_t)G * lvl * sizeof(ge)));
+    CTX_TRY(ctx->lvlQ.ensure(2 * (size_t)G * lvl * sizeof(ge)));
+    uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
+    uint32_t *heavy = (uint32_t *)ctx->heavy.p;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 2) * 4, s));
+    CUDA_TRY(cudaMemsetAsync(heavy + nb + 1, 0, 4, s));
+    msm_params P;
+    memcpy(P.seg, plan->seg, sizeof(P.seg));
+    P.nseg = plan->nseg; P.total = total; P.ptotal = ctx->ptotal;
+    if (total) {
+        k_msm_digits<0><<<LAUNCH_1D(total, 256), 0, s>>>(P, counts, nullptr);
+        KCHECK();
+    }
+    k_msm_scan<<<1, 1024, 0, s>>>(counts, nb, offsets, cursor);
+    KCHECK();
+    if (total) {
+        k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
+        KCHECK();
+        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p);
+        KCHECK();
+    }
+    k_msm_finish<<<LAUNCH_1D(nb, 128), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1);
+    KCHECK();
+    if (total) {
+        k_msm_heavy<<<64, 128, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1);
+        KCHECK();
+    }
+    // weighted sum: 32800 -> 8200 -> 2050 -> 513 -> (tail) 1
+    ge *PA = (ge *)ctx->lvlP.p, *PB = PA + (size_t)G * lvl, *QA = (ge *)ctx->lvlQ.p, *QB = QA + (size_t)G * lvl;
+    uint32_t n = BPG_NBP;
+    k_msm_wsum_level<<<dim3((n / 4 + 127) / 128, G), 128, 0, s>>>((const ge *)ctx->buckets.p, nullptr, n, BPG_NBP, PA, QA, (uint32_t)lvl);
+    KCHECK();
+    n = (n + 3) / 4;
+    k_msm_wsum_level<<<dim3((n / 4 + 128) / 128, G), 128, 0, s>>>(PA, QA, n, (uint32_t)lvl, PB, QB, (uint32_t)lvl);
+    KCHECK();
+    n = (n + 3) / 4;
+    k_msm_wsum_level<<<dim3((n / 4 + 128) / 128, G), 128, 0, s>>>(PB, QB, n, (uint32_t)lvl, PA, QA, (uint32_t)lvl);
+    KCHECK();
+    n = (n + 3) / 4;
+    k_msm_wsum_tail<<<G, 128, 0, s>>>(PA, QA, n, (uint32_t)lvl, PB, QB, d_out);
+    KCHECK();
+    return BPG_OK;
+}
+
+// ================================================================ Pedersen / MSM entry points
+extern "C" int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t *r, size_t n, uint8_t *out32) {
+    if (!ctx || (n && (!v || !r || !out32))) return BPG_E_ARG;
+    if (!ctx->cap) CTX_TRY(bpg_gens_ensure(ctx, 64));
+    if (!n) return BPG_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->scratch[0].ensure(96 * n));
+    uint8_t *d = (uint8_t *)ctx->scratch[0].p;
+    CUDA_TRY(cudaMemcpyAsync(d, v, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d + 32 * n, r, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_pedersen_kernel<<<LAUNCH_1D(n, 128), 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
+    KCHECK();
+    CUDA_TRY(cudaMemcpyAsync(out32, d + 64 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
+
+// variable-base part: decompress + per-term windowed scalar multiplication + tree sum -> d_out (1 point)
+static int varbase_msm_dev(bpg_ctx *ctx, cudaStream_t s, const uint8_t *d_scalars, const uint8_t *d_points32, size_t k, ge *d_out, uint32_t *d_ok,
+                           dev_buf &pts_buf, dev_buf &blk_buf) {
+    CTX_TRY(pts_buf.ensure((k + 1) * sizeof(ge)));
+    size_t nb = (k + 63) / 64;
+    CTX_TRY(blk_buf.ensure(2 * (nb + 64) * sizeof(ge)));
+    ge *pts = (ge *)pts_buf.p, *blk = (ge *)blk_buf.p;
+    k_decompress_kernel<<<LAUNCH_1D(k, 128), 0, s>>>(d_points32, (uint32_t)k, pts, d_ok);
+    KCHECK();
+    k_varbase_kernel<<<(unsigned)nb, 64, 0, s>>>((const sc *)d_scalars, pts, (uint32_t)k, blk);
+    KCHECK();
+    return run_points_sum(ctx, s, blk, nb, blk + nb + 32, d_out);
+}
+
+static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const uint8_t *h_sG, const uint8_t *h_sH, size_t n, size_t offset,
+                         const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t *out32, uint8_t *out128) {
+    if (!ctx) return BPG_E_ARG;
+    if (k && (!extra_scalars || !extra_points32)) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (offset + n > ctx->cap) return BPG_E_SIZE;
+    if (!ctx->cap) CTX_TRY(bpg_gens_ensure(ctx, 64));
+    cudaStream_t s = ctx->stream;
+    // stage host inputs
+    size_t nG = (d_sG || h_sG) ? n : 0, nH = (d_sH || h_sH) ? n : 0;
+    size_t hbytes = 32 * ((h_sG ? n : 0) + (h_sH ? n : 0)) + 64 * k;
+    CTX_TRY(ctx->scratch[2].ensure(hbytes + 64));
+    uint8_t *d = (uint8_t *)ctx->scratch[2].p;
+    size_t off = 0;
+    if (h_sG) { CUDA_TRY(cudaMemcpyAsync(d + off, h_sG, 32 * n, cudaMemcpyHostToDevice, s)); d_sG = d + off; off += 32 * n; }
+    if (h_sH) { CUDA_TRY(cudaMemcpyAsync(d + off, h_sH, 32 * n, cudaMemcpyHostToDevice, s)); d_sH = d + off; off += 32 * n; }
+    const uint8_t *d_es = nullptr, *d_ep = nullptr;
+    if (k) {
+        CUDA_TRY(cudaMemcpyAsync(d + off, extra_scalars, 32 * k, cudaMemcpyHostToDevice, s)); d_es = d + off; off += 32 * k;
+        CUDA_TRY(cudaMemcpyAsync(d + off, extra_points32, 32 * k, cudaMemcpyHostToDevice, s)); d_ep = d + off; off += 32 * k;
+    }
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    ge *res = (ge *)ctx->results.p;
+    uint32_t *d_ok = (uint32_t *)(res + 8);
+    uint32_t one = 1;
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
+    msm_plan plan;
+    memset(&plan, 0, sizeof plan);
+    plan.ngroups = 1;
+    bool host_scalars = h_sG || h_sH;
+    if (nG) { msm_seg &g = plan.seg[plan.nseg++]; g.scalars = (const sc *)d_sG; g.n = (uint32_t)n; g.p0 = (uint32_t)offset; g.group = 0; g.reduce = host_scalars || true; }
+    if (nH) { msm_seg &g = plan.seg[plan.nseg++]; g.scalars = (const sc *)d_sH; g.n = (uint32_t)n; g.p0 = (uint32_t)(ctx->cap + offset); g.group = 0; g.reduce = host_scalars || true; }
+    CTX_TRY(msm_run(ctx, s, &plan, res));
+    size_t npts = 1;
+    if (k) {
+        CTX_TRY(varbase_msm_dev(ctx, s, d_es, d_ep, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
+        npts = 2;
+    }
+    if (npts == 2) { k_points_sum_kernel<<<1, 64, 0, s>>>(res, 2, res + 2); KCHECK(); }
+    ge *final_pt = npts == 2 ? res + 2 : res;
+    uint32_t ok = 1;
+    if (out32) {
+        uint8_t *d32 = (uint8_t *)(res + 4);
+        CTX_TRY(run_compress(ctx, s, final_pt, 1, d32));
+        CUDA_TRY(cudaMemcpyAsync(out32, d32, 32, cudaMemcpyDeviceToHost, s));
+    }
+    if (out128) CUDA_TRY(cudaMemcpyAsync(out128, final_pt, 128, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ok ? BPG_OK : BPG_E_DECOMPRESS;
+}
+extern "C" int bpg_msm_gens(bpg_ctx *ctx, const uint8_t *sG, const uint8_t *sH, size_t n, size_t offset, const uint8_t *extra_scalars,
+                            const uint8_t *extra_points32, size_t k, uint8_t out32[32]) {
+    if (!out32) return BPG_E_ARG;
+    return msm_gens_impl(ctx, nullptr, nullptr, sG, sH, n, offset, extra_scalars, extra_points32, k, out32, nullptr);
+}
+extern "C" int bpg_msm_gens_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out32[32]) {
+    if (!out32) return BPG_E_ARG;
+    return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n, offset, nullptr, nullptr, 0, out32, nullptr);
+}
+extern "C" int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out128[128]) {
+    if (!out128) return BPG_E_ARG;
+    return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n, offset, nullptr, nullptr, 0, nullptr, out128);
+}
+extern "C" int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8_t out32[32]) {
+    if (!ctx || !ext128 || !out32 || n == 0 || n > 64) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    CTX_TRY(ctx->scratch[3].ensure(64 * sizeof(ge)));
+    ge *pts = (ge *)ctx->scratch[3].p, *res = (ge *)ctx->results.p;
+    CUDA_TRY(cudaMemcpyAsync(pts, ext128, 128 * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_points_sum_kernel<<<1, 64, 0, ctx->stream>>>(pts, (uint32_t)n, res);
+    KCHECK();
+    CTX_TRY(run_compress(ctx, ctx->stream, res, 1, (uint8_t *)(res + 4)));
+    CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
+extern "C" int bpg_msm(bpg_ctx *ctx, const uint8_t *scalars, const uint8_t *points32, size_t n, uint8_t out32[32]) {
+    if (!ctx || !out32 || (n && (!scalars || !points32))) return BPG_E_ARG;
+    if (n == 0) { memset(out32, 0, 32); return BPG_OK; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CTX_TRY(ctx->scratch[2].ensure(64 * n));
+    uint8_t *d = (uint8_t *)ctx->scratch[2].p;
+    CUDA_TRY(cudaMemcpyAsync(d, scalars, 32 * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d + 32 * n, points32, 32 * n, cudaMemcpyHostToDevice, s));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    ge *res = (ge *)ctx->results.p;
+    uint32_t *d_ok = (uint32_t *)(res + 8);
+    uint32_t one = 1, ok = 1;
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
+    CTX_TRY(varbase_msm_dev(ctx, s, d, d + 32 * n, n, res, d_ok, ctx->scratch[3], ctx->scratch[4]));
+    CTX_TRY(run_compress(ctx, s, res, 1, (uint8_t *)(res + 4)));
+    CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ok ? BPG_OK : BPG_E_DECOMPRESS;
+}
+extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t sr[32], const uint8_t *PL32, const uint8_t *PR32, size_t n, uint8_t *out32) {
+    if (!ctx || !sl || !sr || (n && (!PL32 || !PR32 || !out32))) return BPG_E_ARG;
+    if (!n) return BPG_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CTX_TRY(ctx->scratch[2].ensure(96 * n + 128));
+    CTX_TRY(ctx->scratch[3].ensure(3 * n * sizeof(ge)));
+    uint8_t *d = (uint8_t *)ctx->scratch[2].p;
+    ge *pts = (ge *)ctx->scratch[3].p;
+    CUDA_TRY(cudaMemcpyAsync(d, sl, 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d + 32, sr, 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d + 64, PL32, 32 * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d + 64 + 32 * n, PR32, 32 * n, cudaMemcpyHostToDevice, s));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    uint32_t *d_ok = (uint32_t *)((ge *)ctx->results.p + 8);
+    uint32_t one = 1, ok = 1;
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
+    k_decompress_kernel<<<LAUNCH_1D(2 * n, 128), 0, s>>>(d + 64, (uint32_t)(2 * n), pts, d_ok);
+    KCHECK();
+    k_fold_kernel<<<LAUNCH_1D(n, 64), 0, s>>>((const sc *)d, (const sc *)(d + 32), pts, pts + n, (uint32_t)n, pts + 2 * n);
+    KCHECK();
+    CTX_TRY(run_compress(ctx, s, pts + 2 * n, n, d + 64));
+    CUDA_TRY(cudaMemcpyAsync(out32, d + 64, 32 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ok ? BPG_OK : BPG_E_DECOMPRESS;
+}
+
+extern "C" int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32) {
+    if (!ctx || !ms || !mac32) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    int blocks = sms * 8, threads = 256;
+    CTX_TRY(ctx->scratch[5].ensure((size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    k_bench_fe_mul<<<blocks, threads, 0, ctx->stream>>>((uint32_t *)ctx->scratch[5].p, 8); // warm-up
+    KCHECK();
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    k_bench_fe_mul<<<blocks, threads, 0, ctx->stream>>>((uint32_t *)ctx->scratch[5].p, iters);
+    KCHECK();
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *mac32 = (double)blocks * threads * (double)iters * 2.0 * 72.0; // 64 limb products + 8 fold-by-38 per field multiply
+    return BPG_OK;
+}
+
+// ================================================================ Merlin transcript (host)
+struct bpg_transcript { bpgh::Transcript t; };
+extern "C" bpg_transcript *bpg_transcript_new(const uint8_t *label, size_t len) { bpg_transcript *t = new bpg_transcript(); t->t = bpgh::Transcript(label, len); return t; }
+extern "C" void bpg_transcript_free(bpg_transcript *t) { delete t; }
+extern "C" void bpg_transcript_append(bpg_transcript *t, const uint8_t *label, size_t ll, const uint8_t *msg, size_t ml) { t->t.append_raw(label, ll, msg, ml); }
+extern "C" void bpg_transcript_challenge(bpg_transcript *t, const uint8_t *label, size_t ll, uint8_t *out, size_t n) { t->t.challenge_raw(label, ll, out, n); }
+
+#include "prover.inl"

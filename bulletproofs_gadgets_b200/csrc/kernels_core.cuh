@@ -1,0 +1,301 @@
+// kernels_core.cuh -- generator derivation, resident window tables, compression, Pedersen comb.
+// (included by bpg.cu; device code for sm_100a)
+#pragma once
+#include "bpg_internal.h"
+
+bpg_consts h_K;
+
+#define LAUNCH_1D(n, bs) dim3((unsigned)(((n) + (bs)-1) / (bs))), dim3(bs)
+
+// ---- 128-bit vectorised loads/stores of field elements (all structures are 32-byte aligned)
+__device__ __forceinline__ void ld_fe(fe &r, const fe *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void ld_fe_nc(fe &r, const fe *p) { // plain (coherent) load for data written earlier in the same job
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st_fe(fe *p, const fe &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void ld_sc(sc &r, const sc *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st_sc(sc *p, const sc &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void ld_an(ge_an &r, const ge_an *p) { ld_fe(r.ypx, &p->ypx); ld_fe(r.ymx, &p->ymx); ld_fe(r.t2d, &p->t2d); }
+__device__ __forceinline__ void st_an(ge_an *p, const ge_an &r) { st_fe(&p->ypx, r.ypx); st_fe(&p->ymx, r.ymx); st_fe(&p->t2d, r.t2d); }
+__device__ __forceinline__ void ld_ge(ge &r, const ge *p) { ld_fe_nc(r.X, &p->X); ld_fe_nc(r.Y, &p->Y); ld_fe_nc(r.Z, &p->Z); ld_fe_nc(r.T, &p->T); }
+__device__ __forceinline__ void st_ge(ge *p, const ge &r) { st_fe(&p->X, r.X); st_fe(&p->Y, r.Y); st_fe(&p->Z, r.Z); st_fe(&p->T, r.T); }
+
+// extended -> affine Niels (one inversion)
+__device__ __forceinline__ void ge_to_an(ge_an &o, const ge &p) {
+    fe zi, x, y;
+    fe_invert(zi, p.Z);
+    fe_mul(x, p.X, zi);
+    fe_mul(y, p.Y, zi);
+    ge_affine_to_an(o, x, y);
+}
+// affine Niels -> extended without a division: (X:Y:Z:T) = (2(ypx-ymx) : 2(ypx+ymx) : 4 : (ypx-ymx)(ypx+ymx))
+__device__ __forceinline__ void an_to_ge(ge &o, const ge_an &p) {
+    fe dx, sy;
+    fe_sub(dx, p.ypx, p.ymx);
+    fe_add(sy, p.ypx, p.ymx);
+    fe_dbl(o.X, dx);
+    fe_dbl(o.Y, sy);
+    fe_set0(o.Z); o.Z.v[0] = 4;
+    fe_mul(o.T, dx, sy);
+}
+
+// ---------------------------------------------------------------- generator derivation + window tables (K7)
+// stream: 64 bytes per point (SHAKE256 "GeneratorsChain" output, or any uniform bytes).  One thread per point:
+// double-Elligator, then for each of the 16 windows store the affine-Niels form and double 16 times.
+__global__ void __launch_bounds__(128) k_gens_tables(const uint8_t *__restrict__ stream, uint32_t npoints, uint32_t p0, uint32_t ptotal,
+                                                     ge_an *__restrict__ tab) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npoints) return;
+    uint8_t b[64];
+    const uint4 *src = reinterpret_cast<const uint4 *>(stream + 64ull * i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint4 v = __ldg(src + k); memcpy(b + 16 * k, &v, 16); }
+    ge p;
+    ge_from_uniform_bytes(p, b);
+#pragma unroll 1
+    for (int w = 0; w < BPG_NWIN; w++) {
+        ge_an a;
+        ge_to_an(a, p);
+        st_an(&tab[(size_t)w * ptotal + p0 + i], a);
+        if (w + 1 < BPG_NWIN) {
+#pragma unroll 1
+            for (int k = 0; k < BPG_WBITS; k++) ge_dbl(p, p);
+        }
+    }
+}
+// same for points given as 32-byte ristretto encodings (B); B~ = from_uniform_bytes(SHA3-512(B)) uses the kernel above
+__global__ void k_point_tables(const uint8_t *__restrict__ enc32, uint32_t npoints, uint32_t p0, uint32_t ptotal, ge_an *__restrict__ tab,
+                               uint32_t *ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npoints) return;
+    uint8_t b[32];
+    for (int k = 0; k < 32; k++) b[k] = enc32[32 * i + k];
+    ge p;
+    if (!ristretto_decode(p, b)) { atomicAnd(ok, 0u); return; }
+#pragma unroll 1
+    for (int w = 0; w < BPG_NWIN; w++) {
+        ge_an a;
+        ge_to_an(a, p);
+        st_an(&tab[(size_t)w * ptotal + p0 + i], a);
+        if (w + 1 < BPG_NWIN) {
+#pragma unroll 1
+            for (int k = 0; k < BPG_WBITS; k++) ge_dbl(p, p);
+        }
+    }
+}
+// signed 8-bit comb for the two Pedersen bases: comb[b][w][j] = (j+1) * 2^(8w) * base_b, j in [0,128), w in [0,32)
+__global__ void k_build_comb(const ge_an *__restrict__ tab, uint32_t ptotal, uint32_t pB, ge_an *__restrict__ comb) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; // (base, w)
+    if (t >= 64) return;
+    uint32_t b = t >> 5, w = t & 31;
+    // 2^(8w) * base : even w from the 16-bit window table, odd w by 8 doublings
+    ge_an a0;
+    ld_an(a0, &tab[(size_t)(w >> 1) * ptotal + pB + b]);
+    ge p;
+    an_to_ge(p, a0);
+    if (w & 1) {
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) ge_dbl(p, p);
+    }
+    ge_an base;
+    ge_to_an(base, p);
+    ge cur = p;
+#pragma unroll 1
+    for (int j = 0; j < 128; j++) {
+        ge_an a;
+        ge_to_an(a, cur);
+        st_an(&comb[((size_t)b * 32 + w) * 128 + j], a);
+        ge_add_an(cur, cur, base);
+    }
+}
+
+// ---------------------------------------------------------------- compression
+__global__ void __launch_bounds__(128) k_compress_kernel(const ge *__restrict__ pts, uint32_t n, uint8_t *__restrict__ out32) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge p;
+    ld_ge(p, &pts[i]);
+    uint8_t b[32];
+    ristretto_encode(b, p);
+    uint4 *dst = reinterpret_cast<uint4 *>(out32 + 32ull * i);
+    uint4 v0, v1;
+    memcpy(&v0, b, 16); memcpy(&v1, b + 16, 16);
+    dst[0] = v0; dst[1] = v1;
+}
+__global__ void k_export_kernel(const ge_an *__restrict__ tab, uint32_t p0, uint32_t n, uint8_t *__restrict__ out32) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_an a;
+    ld_an(a, &tab[p0 + i]);
+    ge p;
+    an_to_ge(p, a);
+    uint8_t b[32];
+    ristretto_encode(b, p);
+    for (int k = 0; k < 32; k++) out32[32ull * i + k] = b[k];
+}
+__global__ void __launch_bounds__(128) k_decompress_kernel(const uint8_t *__restrict__ in32, uint32_t n, ge *__restrict__ out, uint32_t *ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    for (int k = 0; k < 32; k++) b[k] = in32[32ull * i + k];
+    ge p;
+    if (!ristretto_decode(p, b)) { atomicAnd(ok, 0u); ge_identity(p); }
+    st_ge(&out[i], p);
+}
+
+// ---------------------------------------------------------------- Pedersen commitments (K3)
+// out[i] = compress(v[i]*B + r[i]*B~): 64 mixed additions from the signed 8-bit comb + one inverse square root.
+__device__ __forceinline__ void sc_signed_bytes(int *d, const sc &k) { // 32 signed radix-256 digits in [-128,127], plus carry folded (k < 2^253)
+    int carry = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int b = (int)((k.v[i >> 2] >> (8 * (i & 3))) & 0xFF) + carry;
+        carry = b >= 128;
+        d[i] = b - (carry << 8);
+    }
+}
+__global__ void __launch_bounds__(128) k_pedersen_kernel(const sc *__restrict__ v, const sc *__restrict__ r, uint32_t n, const ge_an *__restrict__ comb,
+                                                          uint8_t *__restrict__ out32, ge *__restrict__ out_ext) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int b = 0; b < 2; b++) {
+        sc k;
+        ld_sc(k, b == 0 ? &v[i] : &r[i]);
+        sc_reduce(k, k);
+        int d[32];
+        sc_signed_bytes(d, k);
+#pragma unroll 1
+        for (int w = 0; w < 32; w++) {
+            int dw = d[w];
+            if (dw == 0) continue;
+            int mag = dw < 0 ? -dw : dw;
+            ge_an a, na;
+            ld_an(a, &comb[((size_t)b * 32 + w) * 128 + (mag - 1)]);
+            if (dw < 0) { ge_an_neg(na, a); a = na; }
+            ge_add_an(acc, acc, a);
+        }
+    }
+    if (out_ext) st_ge(&out_ext[i], acc);
+    if (out32) {
+        uint8_t e[32];
+        ristretto_encode(e, acc);
+        for (int k = 0; k < 32; k++) out32[32ull * i + k] = e[k];
+    }
+}
+
+// ---------------------------------------------------------------- small variable-base MSM (verifier extras, bpg_msm, fold)
+// one thread per term: 4-bit fixed-window scalar multiplication (table of 8 multiples in local memory), then a
+// block tree reduction; block results are summed by a second launch of k_points_sum_kernel.
+__device__ __forceinline__ void ge_scalarmul_w4(ge &r, const sc &kred, const ge &p) {
+    ge_pn tabl[8];
+    ge cur = p;
+    ge_to_pn(tabl[0], cur);
+#pragma unroll 1
+    for (int j = 1; j < 8; j++) { ge_add_pn(cur, cur, tabl[0]); ge_to_pn(tabl[j], cur); }
+    // signed radix-16 digits, top first
+    signed char dg[64];
+    int carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        int b = (int)((kred.v[i >> 3] >> (4 * (i & 7))) & 0xF) + carry;
+        carry = b >= 8;
+        dg[i] = (signed char)(b - (carry << 4));
+    }
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) { ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); }
+        int d = dg[i];
+        if (d > 0) ge_add_pn(acc, acc, tabl[d - 1]);
+        else if (d < 0) { ge_pn n; ge_pn_neg(n, tabl[-d - 1]); ge_add_pn(acc, acc, n); }
+    }
+    r = acc;
+}
+__device__ __forceinline__ void block_sum_points(ge &acc, ge *smem) { // blockDim.x <= 128 threads, result in thread 0
+    int t = threadIdx.x;
+    st_ge(&smem[t], acc);
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (t < s) {
+            ge a, b;
+            ld_ge(a, &smem[t]); ld_ge(b, &smem[t + s]);
+            ge_add(a, a, b);
+            st_ge(&smem[t], a);
+        }
+        __syncthreads();
+    }
+    if (t == 0) ld_ge(acc, &smem[0]);
+}
+__global__ void __launch_bounds__(64) k_varbase_kernel(const sc *__restrict__ scalars, const ge *__restrict__ pts, uint32_t n, ge *__restrict__ block_out) {
+    __shared__ ge smem[64];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    ge acc;
+    ge_identity(acc);
+    if (i < n) {
+        sc k; ld_sc(k, &scalars[i]); sc_reduce(k, k);
+        ge p; ld_ge(p, &pts[i]);
+        ge_scalarmul_w4(acc, k, p);
+    }
+    block_sum_points(acc, smem);
+    if (threadIdx.x == 0) st_ge(&block_out[blockIdx.x], acc);
+}
+// out[blockIdx] = sum of up to 64 consecutive points
+__global__ void __launch_bounds__(64) k_points_sum_kernel(const ge *__restrict__ pts, uint32_t n, ge *__restrict__ block_out) {
+    __shared__ ge smem[64];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    ge acc;
+    if (i < n) ld_ge(acc, &pts[i]); else ge_identity(acc);
+    block_sum_points(acc, smem);
+    if (threadIdx.x == 0) st_ge(&block_out[blockIdx.x], acc);
+}
+// IPP generator fold as a standalone op: out[i] = sl*PL[i] + sr*PR[i]
+__global__ void __launch_bounds__(64) k_fold_kernel(const sc *__restrict__ sl, const sc *__restrict__ sr, const ge *__restrict__ PL, const ge *__restrict__ PR,
+                                                     uint32_t n, ge *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc a, b;
+    ld_sc(a, sl); ld_sc(b, sr);
+    sc_reduce(a, a); sc_reduce(b, b);
+    ge p, q, r1, r2;
+    ld_ge(p, &PL[i]); ld_ge(q, &PR[i]);
+    ge_scalarmul_w4(r1, a, p);
+    ge_scalarmul_w4(r2, b, q);
+    ge_add(r1, r1, r2);
+    st_ge(&out[i], r1);
+}
+
+// ---------------------------------------------------------------- integer-pipe microbenchmark
+__global__ void __launch_bounds__(256) k_bench_fe_mul(uint32_t *out, int iters) {
+    fe a, b;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = t * 2654435761u + i; b.v[i] = t * 40503u + 77u * i + 1; }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) { fe_mul(a, a, b); fe_mul(b, b, a); }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a.v[i] ^ b.v[i];
+    if (x == 0x12345678u) out[t] = x; // keep the chain alive without a store on the common path
+}

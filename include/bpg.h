@@ -1,0 +1,134 @@
+/* bpg.h -- C ABI of libbpg: the B200-native (sm_100a) hot path under the Bulletproofs R1CS prover and
+ * verifier of MarcKloter/bulletproofs_gadgets.
+ *
+ * Each entry point names the reference interface it replaces (file:line under /root/reference; "ext" = the call
+ * lands in the un-vendored crates curve25519-dalek 1.x / bulletproofs `develop` / merlin 1.x, Cargo.toml:8,10,17-20,
+ * so the citation is the reference's call site).  INTEGRATION.md shows the Rust `extern "C"` block and the patch
+ * points in the fork that bind these symbols.
+ *
+ * Conventions
+ *   - scalars: 32-byte little endian.  Inputs follow dalek `Scalar::from_bits` semantics (conversions.rs:18,43):
+ *     any value < 2^256 is accepted and reduced mod l on the device; outputs are canonical (< l).
+ *   - points: 32-byte compressed ristretto255 (dalek CompressedRistretto) unless stated otherwise.
+ *   - return value: BPG_OK (0) or a negative BPG_E_* code; nothing throws or aborts across the ABI.
+ *   - a bpg_ctx is bound to one CUDA device and one stream, and is NOT thread-safe; distinct contexts are
+ *     independent.  The caller owns every host buffer.  No randomness is generated inside the library:
+ *     every random value the reference draws from thread_rng is an explicit input (ext_rng32 / blindings).
+ *   - there is no CPU fallback: every entry point that computes fails with BPG_E_CUDA without a device.
+ */
+#ifndef BPG_H
+#define BPG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPG_OK 0
+#define BPG_E_CUDA (-1)        /* CUDA runtime error (see bpg_last_error) */
+#define BPG_E_SIZE (-2)        /* bad size / capacity (R1CSError::InvalidGeneratorsLength) */
+#define BPG_E_DECOMPRESS (-3)  /* a point encoding failed to decompress */
+#define BPG_E_ARG (-4)         /* null / inconsistent argument */
+#define BPG_E_FORMAT (-5)      /* R1CSProof::from_bytes failure (R1CSError::FormatError) */
+#define BPG_E_NOMEM (-6)
+
+typedef struct bpg_ctx bpg_ctx;
+typedef struct bpg_circuit bpg_circuit;
+
+/* flags for bpg_r1cs_prove / bpg_r1cs_verify */
+#define BPG_FLAG_LEGACY_FRAMING 1u /* proof bytes without the 1-byte phase tag, 14 fixed fields */
+#define BPG_FLAG_FAST_BLINDING 2u  /* s_L, s_R expanded on the device from a transcript-derived seed instead of
+                                      2n sequential Merlin TranscriptRng draws: valid proofs, different bytes */
+
+int bpg_ctx_create(int device, bpg_ctx **out);
+void bpg_ctx_destroy(bpg_ctx *ctx);
+const char *bpg_last_error(bpg_ctx *ctx);
+const char *bpg_strerror(int code);
+/* kernels launched by this context so far (bench.py reports the delta as gpu_launches) */
+uint64_t bpg_launch_count(bpg_ctx *ctx);
+int bpg_sync(bpg_ctx *ctx);
+
+/* BulletproofGens::new(capacity, 1) + PedersenGens::default()  [ext; prover.rs:53,92  verifier.rs:89].
+ * Derives the G/H chains (SHAKE256 stream on the host, double-Elligator on the device) and builds the resident
+ * window tables in HBM.  Idempotent; growing re-derives. */
+int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity);
+size_t bpg_gens_capacity(bpg_ctx *ctx);
+/* compressed generators G[i0..i0+n), H[i0..i0+n) (for parity tests / BulletproofGens accessors) */
+int bpg_gens_export(bpg_ctx *ctx, size_t i0, size_t n, uint8_t *G32, uint8_t *H32);
+int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bblinding32[32]);
+
+/* PedersenGens::commit(v, r) batched: out[i] = compress(v[i]*B + r[i]*B~)
+ * [ext; gadget.rs:31  commitments.rs:27,39  cs_buffer.rs:39  assignment_parser.rs:162] */
+int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t *r, size_t n, uint8_t *out32);
+
+/* RistrettoPoint::vartime_multiscalar_mul / optional_multiscalar_mul over arbitrary points [ext].
+ * BPG_E_DECOMPRESS if any point fails to decode (optional_multiscalar_mul returning None). */
+int bpg_msm(bpg_ctx *ctx, const uint8_t *scalars, const uint8_t *points32, size_t n, uint8_t out32[32]);
+/* sum sG[i]*G[offset+i] + sum sH[i]*H[offset+i] + sum extra_scalars[j]*extra_points[j]  (sG or sH may be NULL):
+ * the shape of every MSM inside Prover::prove / Verifier::verify [ext; prover.rs:93 verifier.rs:90]. */
+int bpg_msm_gens(bpg_ctx *ctx, const uint8_t *sG, const uint8_t *sH, size_t n, size_t offset,
+                 const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t out32[32]);
+/* same, scalars already resident on the device (n x 32 B each, device pointers); used for HBM-resident timing */
+int bpg_msm_gens_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out32[32]);
+/* partial sum as an uncompressed extended point (128 B) for multi-GPU point-range splits, and the combiner */
+int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out128[128]);
+int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8_t out32[32]);
+
+/* One inner-product-argument generator fold: out[i] = sl*PL[i] + sr*PR[i]  (InnerProductProof::create's
+ * G'/H' update, dalek: a 2-point vartime MSM per element) [ext; inside prover.rs:93]. */
+int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t sr[32], const uint8_t *PL32, const uint8_t *PR32,
+                    size_t n, uint8_t *out32);
+
+/* MiMC (src/mimc_hash/mimc.rs:7-97, mimc_consts.rs).  The 486 round constants are data of the reference crate:
+ * the caller installs them once (32-byte LE each, Scalar::from_bits). */
+int bpg_mimc_set_constants(bpg_ctx *ctx, const uint8_t *consts486x32);
+/* mimc_hash(preimage) for n byte strings: data = concatenation, offsets[n+1] byte offsets  [mimc.rs:61-75;
+ * callers prover.rs:171,197,325 verifier.rs:451] */
+int bpg_mimc_hash_batch(bpg_ctx *ctx, const uint8_t *data, const uint64_t *offsets, size_t n, uint8_t *out32);
+/* unpadded sponge over 32-byte LE blocks (Merkle nodes, merkle_tree_gadget.rs:7-12,106): hash i absorbs blocks
+ * [block_off[i], block_off[i+1]).  trace (nullable) receives the in-circuit witness of every absorbed block:
+ * 972 multipliers x (a_L, a_R, a_O) x 32 B in gadget order (mimc_hash_gadget.rs:133-144). */
+int bpg_mimc_sponge_batch(bpg_ctx *ctx, const uint8_t *blocks, const uint32_t *block_off, size_t n, uint8_t *out32,
+                          uint8_t *trace);
+
+/* Constraint system in flat CSR form: constraint r is sum_k coeff[k]*var[k] = 0 for k in [row_ptr[r], row_ptr[r+1]),
+ * term_var = kind << 29 | index with kind 0=a_L 1=a_R 2=a_O 3=V 4=One  (bulletproofs r1cs::Variable /
+ * LinearCombination as recorded by ConstraintSystem::constrain; cs_buffer.rs:89-113).  The library keeps a
+ * column-major copy on the device. */
+int bpg_circuit_create(bpg_ctx *ctx, size_t n_multipliers, size_t m_commitments, size_t q_constraints,
+                       const uint32_t *row_ptr, const uint32_t *term_var, const uint8_t *term_coeff, bpg_circuit **out);
+void bpg_circuit_destroy(bpg_circuit *c);
+
+/* Prover::new(label) + commit(v_i, blinding_i)* + (constraints) + prove(&bp_gens)  [ext; prover.rs:52-54,93
+ * gadget.rs:18-38].  Writes the m commitments to V_out (nullable) and the serialised R1CSProof to `proof`;
+ * returns the proof length (> 0) or a negative BPG_E_* code.  ext_rng32 are the 32 bytes the reference's
+ * TranscriptRngBuilder::finalize draws from thread_rng. */
+long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *aL,
+                    const uint8_t *aR, const uint8_t *aO, const uint8_t *v, const uint8_t *v_blinding,
+                    const uint8_t ext_rng32[32], unsigned flags, uint8_t *V_out, uint8_t *proof, size_t proof_cap);
+/* Verifier::new(label) + commit(V_i)* + (constraints) + verify(&proof,&pc_gens,&bp_gens)  [ext; verifier.rs:51-53,90].
+ * *accept = 1 for Ok(()), 0 for Err(VerificationError | FormatError); the return value only reports library errors. */
+int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32,
+                    const uint8_t *proof, size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept);
+
+/* Merlin transcript (host; sequential Keccak, never on the device) exposed for the Rust shim and the tests */
+typedef struct bpg_transcript bpg_transcript;
+bpg_transcript *bpg_transcript_new(const uint8_t *label, size_t len);
+void bpg_transcript_free(bpg_transcript *t);
+void bpg_transcript_append(bpg_transcript *t, const uint8_t *label, size_t ll, const uint8_t *msg, size_t ml);
+void bpg_transcript_challenge(bpg_transcript *t, const uint8_t *label, size_t ll, uint8_t *out, size_t n);
+
+/* device memory helpers for callers that keep vectors resident (bench, multi-GPU drivers) */
+int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr);
+int bpg_dev_free(bpg_ctx *ctx, void *d_ptr);
+int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+/* integer-pipe microbenchmark: runs `iters` dependent field multiplications per thread over a full-chip grid and
+ * returns elapsed milliseconds (CUDA events) and the number of 32x32->64 multiply-accumulates executed */
+int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
