@@ -28,7 +28,7 @@ struct msm_seg {
     uint32_t group;    // output group
     uint32_t reduce;   // 1: scalars may be >= l (host-supplied, Scalar::from_bits semantics)
     uint32_t start;    // filled by msm_run: global term index of term 0
-    uint32_t pad;
+    uint32_t alt;      // 0, or 1 + k: group ^= bit k of the term's index inside the segment (IPP rounds: left/right halves)
 };
 struct msm_plan { msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total; };
 
@@ -56,24 +56,5 @@ struct bpg_ctx {
     std::string last_error;
 };
 
-// ---- kernels.cu
-int k_upload_constants();
-int k_derive_gens(bpg_ctx *c, const uint8_t *h_stream_G, const uint8_t *h_stream_H, size_t cap);
-int k_compress(bpg_ctx *c, cudaStream_t s, const ge *d_pts, size_t n, uint8_t *d_out32);
-int k_table_point_export(bpg_ctx *c, cudaStream_t s, uint32_t p0, size_t n, uint8_t *d_out32);
-int k_pedersen_commit(bpg_ctx *c, cudaStream_t s, const sc *d_v, const sc *d_r, size_t n, uint8_t *d_out32);
-int k_decompress(bpg_ctx *c, cudaStream_t s, const uint8_t *d_in32, size_t n, ge *d_out, uint32_t *d_ok);
-int k_varbase_msm(bpg_ctx *c, cudaStream_t s, const sc *d_scalars, const ge *d_pts, size_t n, ge *d_out /*1*/);
-int k_fold_points(bpg_ctx *c, cudaStream_t s, const sc *d_sl, const sc *d_sr, const ge *d_PL, const ge *d_PR, size_t n, ge *d_out);
-int k_points_sum(bpg_ctx *c, cudaStream_t s, const ge *d_pts, size_t n, ge *d_out);
-int k_mimc(bpg_ctx *c, cudaStream_t s, const sc *d_blocks, const uint32_t *d_block_off, size_t n_hashes, sc *d_out, sc *d_trace);
-int k_mimc_set_constants(const uint8_t *consts486x32);
-
-// ---- msm.cu
+// bpg.cu
 int msm_run(bpg_ctx *c, cudaStream_t s, msm_plan *plan, ge *d_out /* ngroups extended points */);
-
-// ---- vec.cu : scalar-vector kernels of the R1CS prover / verifier / IPP
-struct csc_dev { const uint32_t *col_ptr; const uint32_t *row; const sc *coeff; }; // per variable kind
-int v_pow_tables(bpg_ctx *c, cudaStream_t s, const sc *d_base /*1*/, uint32_t max_exp, sc *d_lo /*1024*/, sc *d_hi);
-int v_flatten(bpg_ctx *c, cudaStream_t s, csc_dev m, uint32_t ncols, const sc *d_zlo, const sc *d_zhi, int negate, sc *d_out);
-int v_reduce_sum(bpg_ctx *c, cudaStream_t s, const sc *d_partials, uint32_t nparts, uint32_t nsums, sc *d_out);

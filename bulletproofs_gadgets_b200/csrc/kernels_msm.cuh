@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     if (S.reduce) sc_reduce(k, k);
     int d[16];
     sc_digits16(d, k);
-    uint32_t base = S.group * BPG_NBP;
+    uint32_t grp = S.group;
+    if (S.alt) grp ^= (j >> (S.alt - 1)) & 1u;
+    uint32_t base = grp * BPG_NBP;
     uint32_t pidx = S.p0 + j;
 #pragma unroll
     for (int w = 0; w < 16; w++) {

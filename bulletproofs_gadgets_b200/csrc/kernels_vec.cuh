@@ -41,3 +41,296 @@ __global__ void __launch_bounds__(128) k_mimc_sponge(const sc *__restrict__ bloc
     }
     st_sc(&out[i], st);
 }
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ void sc_zero(sc &r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+// base^e from the two-level tables lo[e & 1023] * hi[e >> 10]
+__device__ __forceinline__ void pow_lookup(sc &r, const sc *__restrict__ lo, const sc *__restrict__ hi, uint32_t e) {
+    sc a, b;
+    ld_sc(a, &lo[e & 1023u]);
+    if (e >> 10) { ld_sc(b, &hi[e >> 10]); sc_mul(r, a, b); } else r = a;
+}
+// block-wide sum of NS scalars per thread (blockDim.x == 128); result valid in thread 0
+template <int NS>
+__device__ __forceinline__ void block_sum_scalars(sc *vals, sc *smem /* [NS][128] */) {
+    int t = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < NS; k++) st_sc(&smem[k * 128 + t], vals[k]);
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if (t < s) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                sc a, b;
+                ld_sc(a, &smem[k * 128 + t]); ld_sc(b, &smem[k * 128 + t + s]);
+                sc_add_r(a, a, b);
+                st_sc(&smem[k * 128 + t], a);
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) ld_sc(vals[k], &smem[k * 128]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sc_reduce_inplace(sc *v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc x; ld_sc(x, &v[i]); sc_reduce(x, x); st_sc(&v[i], x);
+}
+// lo[t] = base^t (t < 1024), hi[j] = base^(1024 j) (j < nhi)
+__global__ void __launch_bounds__(128) k_pow_tables(const sc *__restrict__ base, sc *__restrict__ lo, sc *__restrict__ hi, uint32_t nhi) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024 + nhi) return;
+    sc b; ld_sc(b, base);
+    sc r;
+    if (t < 1024) { sc_pow_u32(r, b, t); st_sc(&lo[t], r); }
+    else { sc_pow_u32(r, b, (t - 1024u) << 10); st_sc(&hi[t - 1024], r); }
+}
+// sums `nparts` rows of NS scalars (row-major [nparts][NS]) into out[NS]; one block
+template <int NS>
+__global__ void __launch_bounds__(128) k_sum_partials(const sc *__restrict__ parts, uint32_t nparts, sc *__restrict__ out) {
+    __shared__ sc smem[NS * 128];
+    sc acc[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) sc_zero(acc[k]);
+    for (uint32_t p = threadIdx.x; p < nparts; p += 128) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) { sc x; ld_sc(x, &parts[(size_t)p * NS + k]); sc_add_r(acc[k], acc[k], x); }
+    }
+    block_sum_scalars<NS>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) st_sc(&out[k], acc[k]);
+    }
+}
+
+// ---------------------------------------------------------------- flattened constraints (a4 / a8)
+// Entries are sorted by (virtual) column.  A virtual column is a run of <= 256 entries of one variable; it either
+// writes w[dst] directly or, for variables split over several virtual columns, a partial slot (dst | 1<<31).
+// value = sum_k z^(row_k+1) * coeff_k   (coefficients of V / One columns are stored negated).
+__global__ void __launch_bounds__(128) k_flatten_vcols(const uint32_t *__restrict__ vcol_ptr, const uint32_t *__restrict__ vcol_dst, uint32_t nv,
+                                                        const uint32_t *__restrict__ e_row, const sc *__restrict__ e_coeff,
+                                                        const sc *__restrict__ zlo, const sc *__restrict__ zhi, sc *__restrict__ w, sc *__restrict__ partial) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nv) return;
+    sc acc; sc_zero(acc);
+    uint32_t k0 = vcol_ptr[c], k1 = vcol_ptr[c + 1];
+#pragma unroll 1
+    for (uint32_t k = k0; k < k1; k++) {
+        sc zp, cf, p;
+        pow_lookup(zp, zlo, zhi, e_row[k] + 1u);
+        ld_sc(cf, &e_coeff[k]);
+        sc_mul(p, zp, cf);
+        sc_add_r(acc, acc, p);
+    }
+    uint32_t d = vcol_dst[c];
+    if (d & 0x80000000u) st_sc(&partial[d & 0x7FFFFFFFu], acc); else st_sc(&w[d], acc);
+}
+// one block per split variable: w[col] = sum of its partial slots
+__global__ void __launch_bounds__(128) k_flatten_split(const uint32_t *__restrict__ split /* (col, first, count) x ns */, uint32_t ns,
+                                                        const sc *__restrict__ partial, sc *__restrict__ w) {
+    __shared__ sc smem[128];
+    uint32_t s = blockIdx.x;
+    if (s >= ns) return;
+    uint32_t col = split[3 * s], first = split[3 * s + 1], cnt = split[3 * s + 2];
+    sc acc; sc_zero(acc);
+    for (uint32_t k = threadIdx.x; k < cnt; k += 128) { sc x; ld_sc(x, &partial[first + k]); sc_add_r(acc, acc, x); }
+    block_sum_scalars<1>(&acc, smem);
+    if (threadIdx.x == 0) st_sc(&w[col], acc);
+}
+
+// ---------------------------------------------------------------- prover polynomial phase
+// l1 = aL + y^-i wR ; l2 = aO ; l3 = sL ; r0 = wO - y^i ; r1 = y^i aR + wL ; r3 = y^i sR
+// t1=<l1,r0> t2=<l1,r1>+<l2,r0> t3=<l2,r1>+<l3,r0> t4=<l1,r3>+<l3,r1> t5=<l2,r3> t6=<l3,r3>
+// stores l1,r0,r1,r3 and per-block partial sums of t1..t6.
+__global__ void __launch_bounds__(128) k_poly_phase1(uint32_t n, const sc *__restrict__ aL, const sc *__restrict__ aR, const sc *__restrict__ aO,
+                                                      const sc *__restrict__ sL, const sc *__restrict__ sR, const sc *__restrict__ w /* wL|wR|wO */,
+                                                      const sc *__restrict__ ylo, const sc *__restrict__ yhi, const sc *__restrict__ yilo,
+                                                      const sc *__restrict__ yihi, sc *__restrict__ l1o, sc *__restrict__ r0o, sc *__restrict__ r1o,
+                                                      sc *__restrict__ r3o, sc *__restrict__ tparts /* [grid][6] */) {
+    __shared__ sc smem[6 * 128];
+    sc t[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) sc_zero(t[k]);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        sc yi, yinv, a_l, a_r, a_o, s_l, s_r, wl, wr, wo, l1, r0, r1, r3, p;
+        pow_lookup(yi, ylo, yhi, i);
+        pow_lookup(yinv, yilo, yihi, i);
+        ld_sc(a_l, &aL[i]); ld_sc(a_r, &aR[i]); ld_sc(a_o, &aO[i]); ld_sc(s_l, &sL[i]); ld_sc(s_r, &sR[i]);
+        ld_sc(wl, &w[i]); ld_sc(wr, &w[n + i]); ld_sc(wo, &w[2 * (size_t)n + i]);
+        sc_mul(p, yinv, wr); sc_add_r(l1, a_l, p);
+        sc_sub_r(r0, wo, yi);
+        sc_mul(p, yi, a_r); sc_add_r(r1, p, wl);
+        sc_mul(r3, yi, s_r);
+        st_sc(&l1o[i], l1); st_sc(&r0o[i], r0); st_sc(&r1o[i], r1); st_sc(&r3o[i], r3);
+        sc_mul(p, l1, r0); sc_add_r(t[0], t[0], p);
+        sc_mul(p, l1, r1); sc_add_r(t[1], t[1], p); sc_mul(p, a_o, r0); sc_add_r(t[1], t[1], p);
+        sc_mul(p, a_o, r1); sc_add_r(t[2], t[2], p); sc_mul(p, s_l, r0); sc_add_r(t[2], t[2], p);
+        sc_mul(p, l1, r3); sc_add_r(t[3], t[3], p); sc_mul(p, s_l, r1); sc_add_r(t[3], t[3], p);
+        sc_mul(p, a_o, r3); sc_add_r(t[4], t[4], p);
+        sc_mul(p, s_l, r3); sc_add_r(t[5], t[5], p);
+    }
+    block_sum_scalars<6>(t, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) st_sc(&tparts[(size_t)blockIdx.x * 6 + k], t[k]);
+    }
+}
+// l = x l1 + x^2 l2 + x^3 l3 ; r = r0 + x r1 + x^3 r3 ; padding: l = 0, r = -y^i.
+// Also initialises the per-generator IPP factors EG = G_factors, EH = H_factors (1 or u, times y^-i for H).
+// xs = [x, x^2, x^3, u]
+__global__ void __launch_bounds__(128) k_poly_phase2(uint32_t n, uint32_t N, const sc *__restrict__ xs, const sc *__restrict__ l1, const sc *__restrict__ aO,
+                                                      const sc *__restrict__ sL, const sc *__restrict__ r0, const sc *__restrict__ r1, const sc *__restrict__ r3,
+                                                      const sc *__restrict__ ylo, const sc *__restrict__ yhi, const sc *__restrict__ yilo,
+                                                      const sc *__restrict__ yihi, sc *__restrict__ a, sc *__restrict__ b, sc *__restrict__ EG, sc *__restrict__ EH) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    sc x, x2, x3, u, yinv;
+    ld_sc(x, &xs[0]); ld_sc(x2, &xs[1]); ld_sc(x3, &xs[2]); ld_sc(u, &xs[3]);
+    pow_lookup(yinv, yilo, yihi, i);
+    sc one; sc_set_u32(one, 1);
+    if (i < n) {
+        sc v, p, acc;
+        ld_sc(v, &l1[i]); sc_mul(acc, x, v);
+        ld_sc(v, &aO[i]); sc_mul(p, x2, v); sc_add_r(acc, acc, p);
+        ld_sc(v, &sL[i]); sc_mul(p, x3, v); sc_add_r(acc, acc, p);
+        st_sc(&a[i], acc);
+        ld_sc(acc, &r0[i]);
+        ld_sc(v, &r1[i]); sc_mul(p, x, v); sc_add_r(acc, acc, p);
+        ld_sc(v, &r3[i]); sc_mul(p, x3, v); sc_add_r(acc, acc, p);
+        st_sc(&b[i], acc);
+        st_sc(&EG[i], one);
+        st_sc(&EH[i], yinv);
+    } else {
+        sc z, yi, ny, eh;
+        sc_zero(z);
+        pow_lookup(yi, ylo, yhi, i);
+        sc_neg_r(ny, yi);
+        st_sc(&a[i], z);
+        st_sc(&b[i], ny);
+        st_sc(&EG[i], u);
+        sc_mul(eh, yinv, u);
+        st_sc(&EH[i], eh);
+    }
+}
+
+// ---------------------------------------------------------------- inner-product argument rounds (a6 / a7)
+// current vectors a,b have length nj = 2h.  cparts[block] = (<a_lo,b_hi>, <a_hi,b_lo>)
+__global__ void __launch_bounds__(128) k_ipp_cross(uint32_t h, const sc *__restrict__ a, const sc *__restrict__ b, sc *__restrict__ cparts) {
+    __shared__ sc smem[2 * 128];
+    sc t[2];
+    sc_zero(t[0]); sc_zero(t[1]);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < h; i += gridDim.x * blockDim.x) {
+        sc al, ah, bl, bh, p;
+        ld_sc(al, &a[i]); ld_sc(ah, &a[h + i]); ld_sc(bl, &b[i]); ld_sc(bh, &b[h + i]);
+        sc_mul(p, al, bh); sc_add_r(t[0], t[0], p);
+        sc_mul(p, ah, bl); sc_add_r(t[1], t[1], p);
+    }
+    block_sum_scalars<2>(t, smem);
+    if (threadIdx.x == 0) { st_sc(&cparts[2 * (size_t)blockIdx.x], t[0]); st_sc(&cparts[2 * (size_t)blockIdx.x + 1], t[1]); }
+}
+// out[0] = cL * w, out[1] = cR * w   (scalars of the Q = w*B terms of L and R)
+__global__ void k_ipp_cw(const sc *__restrict__ c2, const sc *__restrict__ w, sc *__restrict__ out) {
+    if (threadIdx.x >= 2 || blockIdx.x) return;
+    sc c, ww, r;
+    ld_sc(c, &c2[threadIdx.x]); ld_sc(ww, w);
+    sc_mul(r, c, ww);
+    st_sc(&out[threadIdx.x], r);
+}
+// Scalars of the round's two MSMs over the ORIGINAL generators (no folded generators are materialised):
+// with r = i mod nj:  r >= h:  G_i -> L with a[r-h]*EG[i],  H_i -> R with b[r-h]*EH[i]
+//                     r <  h:  G_i -> R with a[h+r]*EG[i],  H_i -> L with b[h+r]*EH[i]
+__global__ void __launch_bounds__(128) k_ipp_expand(uint32_t N, uint32_t nj, const sc *__restrict__ a, const sc *__restrict__ b, const sc *__restrict__ EG,
+                                                     const sc *__restrict__ EH, sc *__restrict__ sG, sc *__restrict__ sH) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t h = nj >> 1, r = i & (nj - 1);
+    uint32_t src = r >= h ? r - h : r + h;
+    sc av, bv, eg, eh, p;
+    ld_sc(av, &a[src]); ld_sc(bv, &b[src]); ld_sc(eg, &EG[i]); ld_sc(eh, &EH[i]);
+    sc_mul(p, av, eg); st_sc(&sG[i], p);
+    sc_mul(p, bv, eh); st_sc(&sH[i], p);
+}
+// a' = a_lo u + a_hi u^-1 ; b' = b_lo u^-1 + b_hi u ; EG[i] *= (right half ? u : u^-1) ; EH[i] *= (right half ? u^-1 : u)
+// uu = [u, u^-1]
+__global__ void __launch_bounds__(128) k_ipp_fold(uint32_t N, uint32_t nj, const sc *__restrict__ uu, sc *__restrict__ a, sc *__restrict__ b, sc *__restrict__ EG,
+                                                   sc *__restrict__ EH) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t h = nj >> 1;
+    sc u, ui;
+    ld_sc(u, &uu[0]); ld_sc(ui, &uu[1]);
+    bool right = (i & (nj - 1)) >= h;
+    sc e, p;
+    ld_sc(e, &EG[i]); sc_mul(p, e, right ? u : ui); st_sc(&EG[i], p);
+    ld_sc(e, &EH[i]); sc_mul(p, e, right ? ui : u); st_sc(&EH[i], p);
+    if (i < h) {
+        sc lo, hi, q;
+        ld_sc(lo, &a[i]); ld_sc(hi, &a[h + i]);
+        sc_mul(p, lo, u); sc_mul(q, hi, ui); sc_add_r(p, p, q); st_sc(&a[i], p);
+        ld_sc(lo, &b[i]); ld_sc(hi, &b[h + i]);
+        sc_mul(p, lo, ui); sc_mul(q, hi, u); sc_add_r(p, p, q); st_sc(&b[i], p);
+    }
+}
+
+// ---------------------------------------------------------------- verifier scalars (a8)
+// stab_lo[t] = allinv * prod_{bit k of t set} usq[lg-1-k]  (t < 1024, bits k < min(lg,10))
+// stab_hi[j] = prod_{bit k of j set} usq[lg-1-(k+10)]
+__global__ void __launch_bounds__(128) k_s_tables(const sc *__restrict__ usq, const sc *__restrict__ allinv, uint32_t lg, sc *__restrict__ lo,
+                                                   sc *__restrict__ hi, uint32_t nhi) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024 + nhi) return;
+    sc acc;
+    uint32_t idx, shift;
+    if (t < 1024) { ld_sc(acc, allinv); idx = t; shift = 0; } else { sc_set_u32(acc, 1); idx = t - 1024; shift = 10; }
+#pragma unroll 1
+    for (uint32_t k = 0; k < 22; k++) {
+        if (!((idx >> k) & 1u)) continue;
+        uint32_t bit = k + shift;
+        if (bit >= lg) continue;
+        sc f; ld_sc(f, &usq[lg - 1 - bit]);
+        sc_mul(acc, acc, f);
+    }
+    if (t < 1024) st_sc(&lo[t], acc); else st_sc(&hi[t - 1024], acc);
+}
+// g_i = uf (x y^-i wR_i - a s_i) ; h_i = uf (y^-i (x wL_i + wO_i - b s_{N-1-i}) - 1) ; delta partials <y^-i wR_i, wL_i>
+// vs = [x, a, b, u]
+__global__ void __launch_bounds__(128) k_verify_scalars(uint32_t n, uint32_t N, const sc *__restrict__ vs, const sc *__restrict__ w,
+                                                         const sc *__restrict__ yilo, const sc *__restrict__ yihi, const sc *__restrict__ slo,
+                                                         const sc *__restrict__ shi, sc *__restrict__ g, sc *__restrict__ hh, sc *__restrict__ dparts) {
+    __shared__ sc smem[128];
+    sc d; sc_zero(d);
+    sc x, ia, ib, u, one;
+    ld_sc(x, &vs[0]); ld_sc(ia, &vs[1]); ld_sc(ib, &vs[2]); ld_sc(u, &vs[3]);
+    sc_set_u32(one, 1);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        sc yinv, s_i, s_r, p, q, gv, hv;
+        pow_lookup(yinv, yilo, yihi, i);
+        pow_lookup(s_i, slo, shi, i);
+        pow_lookup(s_r, slo, shi, N - 1 - i);
+        sc_mul(p, ia, s_i);
+        sc_mul(q, ib, s_r);
+        if (i < n) {
+            sc wl, wr, wo, ywr, t;
+            ld_sc(wl, &w[i]); ld_sc(wr, &w[n + i]); ld_sc(wo, &w[2 * (size_t)n + i]);
+            sc_mul(ywr, yinv, wr);
+            sc_mul(t, ywr, wl); sc_add_r(d, d, t);
+            sc_mul(t, x, ywr); sc_sub_r(gv, t, p);
+            sc_mul(t, x, wl); sc_add_r(t, t, wo); sc_sub_r(t, t, q); sc_mul(hv, yinv, t); sc_sub_r(hv, hv, one);
+        } else {
+            sc z, t; sc_zero(z);
+            sc_sub_r(gv, z, p);
+            sc_sub_r(t, z, q); sc_mul(hv, yinv, t); sc_sub_r(hv, hv, one);
+            sc_mul(gv, gv, u); sc_mul(hv, hv, u);
+        }
+        st_sc(&g[i], gv); st_sc(&hh[i], hv);
+    }
+    block_sum_scalars<1>(&d, smem);
+    if (threadIdx.x == 0) st_sc(&dparts[blockIdx.x], d);
+}

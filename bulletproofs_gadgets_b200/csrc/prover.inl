@@ -59,10 +59,492 @@ extern "C" int bpg_mimc_hash_batch(bpg_ctx *ctx, const uint8_t *data, const uint
     return bpg_mimc_sponge_batch(ctx, blocks.data(), boff.data(), n, out32, nullptr);
 }
 
-// ================================================================ R1CS (filled in below)
-struct bpg_circuit { int dummy; };
-extern "C" int bpg_circuit_create(bpg_ctx *, size_t, size_t, size_t, const uint32_t *, const uint32_t *, const uint8_t *, bpg_circuit **) { return BPG_E_ARG; }
-extern "C" void bpg_circuit_destroy(bpg_circuit *) {}
-extern "C" long bpg_r1cs_prove(bpg_ctx *, bpg_circuit *, const uint8_t *, size_t, const uint8_t *, const uint8_t *, const uint8_t *, const uint8_t *,
-                               const uint8_t *, const uint8_t *, unsigned, uint8_t *, uint8_t *, size_t) { return BPG_E_ARG; }
-extern "C" int bpg_r1cs_verify(bpg_ctx *, bpg_circuit *, const uint8_t *, size_t, const uint8_t *, const uint8_t *, size_t, const uint8_t *, unsigned, int *) { return BPG_E_ARG; }
+// ================================================================ R1CS circuit (flattened-constraint matrix, column-major on the device)
+#define BPG_VCOL 256u
+struct bpg_circuit {
+    bpg_ctx *ctx;
+    size_t n, m, q, T;
+    uint32_t ncols;              // 3n + m + 1 : wL | wR | wO | wV | wc
+    uint32_t nv, nsplit, npartial;
+    uint32_t *d_vcol_ptr = nullptr, *d_vcol_dst = nullptr, *d_row = nullptr, *d_split = nullptr;
+    sc *d_coeff = nullptr;
+};
+extern "C" int bpg_circuit_create(bpg_ctx *ctx, size_t n, size_t m, size_t q, const uint32_t *row_ptr, const uint32_t *term_var,
+                                  const uint8_t *term_coeff, bpg_circuit **out) {
+    if (!ctx || !out || !row_ptr || (q && row_ptr[q] && (!term_var || !term_coeff))) return BPG_E_ARG;
+    *out = nullptr;
+    if (n >= (1u << 22) || m >= (1u << 22)) return BPG_E_SIZE;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    size_t T = row_ptr[q];
+    uint32_t ncols = (uint32_t)(3 * n + m + 1);
+    // column of each term, counting sort by column (stable => rows ascending inside a column)
+    std::vector<uint32_t> col_of(T), cnt(ncols + 1, 0);
+    for (size_t k = 0; k < T; k++) {
+        uint32_t kind = term_var[k] >> 29, idx = term_var[k] & 0x1FFFFFFFu, c;
+        if (kind <= 2) { if (idx >= n) return BPG_E_ARG; c = (uint32_t)(kind * n + idx); }
+        else if (kind == 3) { if (idx >= m) return BPG_E_ARG; c = (uint32_t)(3 * n + idx); }
+        else if (kind == 4) c = (uint32_t)(3 * n + m);
+        else return BPG_E_ARG;
+        col_of[k] = c;
+        cnt[c + 1]++;
+    }
+    for (uint32_t c = 0; c < ncols; c++) cnt[c + 1] += cnt[c];
+    std::vector<uint32_t> e_row(T ? T : 1), pos(cnt.begin(), cnt.end() - 1);
+    std::vector<sc> e_coeff(T ? T : 1);
+    for (size_t r = 0; r < q; r++)
+        for (uint32_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+            uint32_t c = col_of[k], p = pos[c]++;
+            e_row[p] = (uint32_t)r;
+            sc cf, red;
+            sc_frombytes(cf, term_coeff + 32 * (size_t)k);
+            sc_reduce(red, cf);
+            if (c >= 3 * n) sc_neg_r(red, red); // wV and wc accumulate -z^k * coeff
+            e_coeff[p] = red;
+        }
+    // virtual columns of <= BPG_VCOL entries
+    std::vector<uint32_t> vptr, vdst, split;
+    vptr.push_back(0);
+    uint32_t npartial = 0;
+    for (uint32_t c = 0; c < ncols; c++) {
+        uint32_t k0 = cnt[c], k1 = cnt[c + 1], len = k1 - k0;
+        if (len <= BPG_VCOL) { vptr.push_back(k1); vdst.push_back(c); continue; } // also writes zero for empty columns
+        uint32_t parts = (len + BPG_VCOL - 1) / BPG_VCOL;
+        split.push_back(c); split.push_back(npartial); split.push_back(parts);
+        for (uint32_t p = 0; p < parts; p++) { vptr.push_back(std::min(k1, k0 + (p + 1) * BPG_VCOL)); vdst.push_back(0x80000000u | npartial++); }
+    }
+    bpg_circuit *c = new bpg_circuit();
+    c->ctx = ctx; c->n = n; c->m = m; c->q = q; c->T = T; c->ncols = ncols;
+    c->nv = (uint32_t)vdst.size(); c->nsplit = (uint32_t)(split.size() / 3); c->npartial = npartial;
+    if (split.empty()) split.push_back(0);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void **d, const void *h, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(d, bytes ? bytes : 4);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void **)&c->d_vcol_ptr, vptr.data(), vptr.size() * 4);
+    up((void **)&c->d_vcol_dst, vdst.data(), vdst.size() * 4);
+    up((void **)&c->d_row, e_row.data(), e_row.size() * 4);
+    up((void **)&c->d_coeff, e_coeff.data(), e_coeff.size() * sizeof(sc));
+    up((void **)&c->d_split, split.data(), split.size() * 4);
+    if (e != cudaSuccess) { bpg_set_cuda_error(e, __FILE__, __LINE__); ctx->last_error = g_cuda_err; bpg_circuit_destroy(c); return BPG_E_CUDA; }
+    *out = c;
+    return BPG_OK;
+}
+extern "C" void bpg_circuit_destroy(bpg_circuit *c) {
+    if (!c) return;
+    cudaFree(c->d_vcol_ptr); cudaFree(c->d_vcol_dst); cudaFree(c->d_row); cudaFree(c->d_coeff); cudaFree(c->d_split);
+    delete c;
+}
+
+// ================================================================ host scalar helpers
+namespace {
+const sc SC_ONE_H = {{1, 0, 0, 0, 0, 0, 0, 0}};
+inline sc h_mul(const sc &a, const sc &b) { sc r; sc_mul(r, a, b); return r; }
+inline sc h_add(const sc &a, const sc &b) { sc r; sc_add_r(r, a, b); return r; }
+inline sc h_sub(const sc &a, const sc &b) { sc r; sc_sub_r(r, a, b); return r; }
+inline sc h_inv(const sc &a) { sc r; sc_invert(r, a); return r; }
+inline sc h_wide(const uint8_t b[64]) {
+    u32 R[16];
+    for (int i = 0; i < 16; i++) R[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
+    sc r; sc_reduce512(r, R); return r;
+}
+inline sc challenge_scalar(bpgh::Transcript &t, const char *label) { uint8_t b[64]; t.challenge(label, b, 64); return h_wide(b); }
+inline sc rng_scalar(bpgh::TranscriptRng &rng) { uint8_t b[64]; rng.fill_bytes(b, 64); return h_wide(b); }
+inline void append_scalar(bpgh::Transcript &t, const char *label, const sc &x) { uint8_t b[32]; sc_tobytes(b, x); t.append(label, b, 32); }
+inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+inline bool sc_canonical_bytes(sc &out, const uint8_t *b) { sc_frombytes(out, b); return !sc_geq_l(out.v); }
+
+// device-side power tables of one base
+struct pow_tab { sc *lo, *hi; };
+int make_pow_tables(bpg_ctx *ctx, cudaStream_t s, const sc *d_base, uint32_t max_exp, sc *d_store, pow_tab &t) {
+    uint32_t nhi = (max_exp >> 10) + 2;
+    t.lo = d_store; t.hi = d_store + 1024;
+    k_pow_tables<<<LAUNCH_1D(1024 + nhi, 128), 0, s>>>(d_base, t.lo, t.hi, nhi);
+    KCHECK();
+    return BPG_OK;
+}
+inline size_t pow_tab_size(uint32_t max_exp) { return 1024 + (max_exp >> 10) + 2; }
+
+int run_flatten(bpg_ctx *ctx, cudaStream_t s, bpg_circuit *c, const pow_tab &z, sc *d_w, dev_buf &partial_buf) {
+    CTX_TRY(partial_buf.ensure(((size_t)c->npartial + 1) * sizeof(sc)));
+    if (c->nv) {
+        k_flatten_vcols<<<LAUNCH_1D(c->nv, 128), 0, s>>>(c->d_vcol_ptr, c->d_vcol_dst, c->nv, c->d_row, c->d_coeff, z.lo, z.hi, d_w, (sc *)partial_buf.p);
+        KCHECK();
+    }
+    if (c->nsplit) {
+        k_flatten_split<<<c->nsplit, 128, 0, s>>>(c->d_split, c->nsplit, (const sc *)partial_buf.p, d_w);
+        KCHECK();
+    }
+    return BPG_OK;
+}
+} // namespace
+
+// ================================================================ Prover::prove
+// Buffer map (ctx->scratch):  8: witness aL|aR|aO|sL|sR (5N)   9: small scalars   10: power tables   11: w (3n+m+1)
+//                            12: l1|r0|r1|r3 (4n) -> later sG|sH (2N)   13: a|b|EG|EH (4N)   14: partial sums   15: flatten partials
+extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *aL, const uint8_t *aR,
+                               const uint8_t *aO, const uint8_t *v, const uint8_t *v_blinding, const uint8_t ext_rng32[32], unsigned flags,
+                               uint8_t *V_out, uint8_t *proof, size_t proof_cap) {
+    if (!ctx || !c || !label || !ext_rng32 || !proof) return BPG_E_ARG;
+    size_t n = c->n, m = c->m;
+    if ((n && (!aL || !aR || !aO)) || (m && (!v || !v_blinding))) return BPG_E_ARG;
+    size_t N = next_pow2(n);
+    int lgN = 0;
+    while (((size_t)1 << lgN) < N) lgN++;
+    bool legacy = flags & BPG_FLAG_LEGACY_FRAMING;
+    size_t need = (legacy ? 0 : 1) + 32 * (size_t)((legacy ? 14 : 11) + 2 * lgN + 2);
+    if (proof_cap < need) return BPG_E_SIZE;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->cap < N) return BPG_E_SIZE; // R1CSError::InvalidGeneratorsLength
+    cudaStream_t s = ctx->stream;
+    const uint32_t pB = (uint32_t)(2 * ctx->cap), pBb = pB + 1;
+
+    bpgh::Transcript t(label, label_len);
+    t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
+    // ---- V_i = v_i B + blinding_i B~  (batched; Prover::commit appends each to the transcript)
+    std::vector<uint8_t> Venc(32 * (m ? m : 1));
+    if (m) CTX_TRY(bpg_pedersen_commit(ctx, v, v_blinding, m, Venc.data()));
+    for (size_t i = 0; i < m; i++) t.append("V", Venc.data() + 32 * i, 32);
+    if (V_out && m) memcpy(V_out, Venc.data(), 32 * m);
+    t.append_u64("m", m);
+    bpgh::TranscriptRng rng(t);
+    for (size_t i = 0; i < m; i++) rng.rekey_with_witness_bytes("v_blinding", v_blinding + 32 * i, 32);
+    rng.finalize(ext_rng32);
+    sc ib = rng_scalar(rng), ob = rng_scalar(rng), sb = rng_scalar(rng);
+
+    // ---- upload the witness, start A_I1 / A_O1 while the host draws s_L, s_R
+    CTX_TRY(ctx->scratch[8].ensure((5 * N + 8) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[9].ensure(256 * sizeof(sc)));
+    sc *d_aL = (sc *)ctx->scratch[8].p, *d_aR = d_aL + N, *d_aO = d_aR + N, *d_sL = d_aO + N, *d_sR = d_sL + N;
+    sc *d_small = (sc *)ctx->scratch[9].p; // [0..2] blindings, [3] y, [4] z, [5] yinv, [6..9] x,x2,x3,u, [10] w, [11..12] u,uinv, [13..14] cL*w,cR*w, [16..] T scalars
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_aL, aL, 32 * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_aR, aR, 32 * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_aO, aO, 32 * n, cudaMemcpyHostToDevice, s));
+        k_sc_reduce_inplace<<<LAUNCH_1D(3 * N, 256), 0, s>>>(d_aL, (uint32_t)(2 * N + n)); // aL|aR|aO regions (N-strided; padding is never read)
+        KCHECK();
+    }
+    sc h_small[3] = {ib, ob, sb};
+    CUDA_TRY(cudaMemcpyAsync(d_small, h_small, sizeof h_small, cudaMemcpyHostToDevice, s));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    CTX_TRY(ctx->scratch[14].ensure(4096 * 6 * sizeof(sc)));
+    ge *res = (ge *)ctx->results.p;
+    uint8_t *d_enc = (uint8_t *)(res + 4);
+    msm_plan plan;
+    memset(&plan, 0, sizeof plan);
+    plan.ngroups = 2;
+    auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0, uint32_t g) {
+        if (!cnt) return;
+        msm_seg &sg = plan.seg[plan.nseg++];
+        sg.scalars = sp; sg.n = (uint32_t)cnt; sg.p0 = p0; sg.group = g; sg.reduce = 0;
+    };
+    add_seg(d_aL, n, 0, 0); add_seg(d_aR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 0, 1, pBb, 0);
+    add_seg(d_aO, n, 0, 1); add_seg(d_small + 1, 1, pBb, 1);
+    CTX_TRY(msm_run(ctx, s, &plan, res));
+    // s_L, s_R: 2n sequential TranscriptRng draws on the host (byte-exact with the reference) ...
+    std::vector<sc> h_s(2 * n + 1);
+    if (flags & BPG_FLAG_FAST_BLINDING) {
+        // ... or a transcript-seeded counter-mode expansion (Keccak-f per element, 8 host threads): valid proofs, other bytes
+        uint8_t seed[32];
+        rng.fill_bytes(seed, 32);
+        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nt; k++)
+            th.emplace_back([&, k] {
+                for (size_t i = k; i < 2 * n; i += nt) {
+                    uint64_t st[25] = {0};
+                    memcpy(st, seed, 32);
+                    st[4] = i; st[5] = 0x1F; st[16] = 0x8000000000000000ULL;
+                    bpgh::keccak_f1600(st);
+                    h_s[i] = h_wide((const uint8_t *)st);
+                }
+            });
+        for (auto &x : th) x.join();
+    } else {
+        for (size_t i = 0; i < 2 * n; i++) h_s[i] = rng_scalar(rng);
+    }
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_sL, h_s.data(), 32 * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_sR, h_s.data() + n, 32 * n, cudaMemcpyHostToDevice, s));
+    }
+    memset(&plan, 0, sizeof plan);
+    plan.ngroups = 1;
+    add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
+    CTX_TRY(msm_run(ctx, s, &plan, res + 2));
+    CTX_TRY(run_compress(ctx, s, res, 3, d_enc));
+    uint8_t AIe[32], AOe[32], Se[32], h_enc[96];
+    CUDA_TRY(cudaMemcpyAsync(h_enc, d_enc, 96, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(AIe, h_enc, 32); memcpy(AOe, h_enc + 32, 32); memcpy(Se, h_enc + 64, 32);
+    t.append("A_I1", AIe, 32); t.append("A_O1", AOe, 32); t.append("S1", Se, 32);
+    t.append("dom-sep", (const uint8_t *)"r1cs-1phase", 11);
+    uint8_t Z32[32] = {0};
+    t.append("A_I2", Z32, 32); t.append("A_O2", Z32, 32); t.append("S2", Z32, 32);
+    sc y = challenge_scalar(t, "y"), z = challenge_scalar(t, "z");
+    sc yinv = h_inv(y);
+
+    // ---- scalar-vector phase on the device
+    size_t ptz = pow_tab_size((uint32_t)c->q + 1), pty = pow_tab_size((uint32_t)N);
+    CTX_TRY(ctx->scratch[10].ensure((ptz + 2 * pty) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[11].ensure(((size_t)c->ncols + 1) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[12].ensure((4 * N + 8) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[13].ensure((4 * N + 8) * sizeof(sc)));
+    sc h3[3] = {y, z, yinv};
+    CUDA_TRY(cudaMemcpyAsync(d_small + 3, h3, sizeof h3, cudaMemcpyHostToDevice, s));
+    pow_tab tz, ty, tyi;
+    sc *d_pt = (sc *)ctx->scratch[10].p;
+    CTX_TRY(make_pow_tables(ctx, s, d_small + 4, (uint32_t)c->q + 1, d_pt, tz));
+    CTX_TRY(make_pow_tables(ctx, s, d_small + 3, (uint32_t)N, d_pt + ptz, ty));
+    CTX_TRY(make_pow_tables(ctx, s, d_small + 5, (uint32_t)N, d_pt + ptz + pty, tyi));
+    sc *d_w = (sc *)ctx->scratch[11].p;
+    CTX_TRY(run_flatten(ctx, s, c, tz, d_w, ctx->scratch[15]));
+    sc *d_l1 = (sc *)ctx->scratch[12].p, *d_r0 = d_l1 + N, *d_r1 = d_r0 + N, *d_r3 = d_r1 + N;
+    sc *d_parts = (sc *)ctx->scratch[14].p;
+    unsigned pb = (unsigned)std::min<size_t>((n + 127) / 128, 1184);
+    sc h_t[6];
+    memset(h_t, 0, sizeof h_t);
+    std::vector<sc> h_wV(m ? m : 1);
+    if (n) {
+        k_poly_phase1<<<pb, 128, 0, s>>>((uint32_t)n, d_aL, d_aR, d_aO, d_sL, d_sR, d_w, ty.lo, ty.hi, tyi.lo, tyi.hi, d_l1, d_r0, d_r1, d_r3, d_parts);
+        KCHECK();
+        k_sum_partials<6><<<1, 128, 0, s>>>(d_parts, pb, d_small + 16);
+        KCHECK();
+        CUDA_TRY(cudaMemcpyAsync(h_t, d_small + 16, sizeof h_t, cudaMemcpyDeviceToHost, s));
+    }
+    if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    sc tb[7];
+    tb[1] = rng_scalar(rng); tb[3] = rng_scalar(rng); tb[4] = rng_scalar(rng); tb[5] = rng_scalar(rng); tb[6] = rng_scalar(rng);
+    // T_1, T_3, T_4, T_5, T_6
+    uint8_t tv8[5 * 32], tbv8[5 * 32], Te[5 * 32];
+    const int TK[5] = {1, 3, 4, 5, 6};
+    for (int k = 0; k < 5; k++) { sc_tobytes(tv8 + 32 * k, h_t[TK[k] - 1]); sc_tobytes(tbv8 + 32 * k, tb[TK[k]]); }
+    CTX_TRY(bpg_pedersen_commit(ctx, tv8, tbv8, 5, Te));
+    static const char *TL[5] = {"T_1", "T_3", "T_4", "T_5", "T_6"};
+    for (int k = 0; k < 5; k++) t.append(TL[k], Te + 32 * k, 32);
+    sc u = challenge_scalar(t, "u"), x = challenge_scalar(t, "x");
+    sc tb2; sc_set_u32(tb2, 0);
+    for (size_t i = 0; i < m; i++) { sc vb, r; sc_frombytes(vb, v_blinding + 32 * i); sc_reduce(r, vb); tb2 = h_add(tb2, h_mul(h_wV[i], r)); }
+    tb[2] = tb2;
+    sc xp[7];
+    xp[0] = SC_ONE_H;
+    for (int k = 1; k <= 6; k++) xp[k] = h_mul(xp[k - 1], x);
+    sc tx, txb;
+    sc_set_u32(tx, 0); sc_set_u32(txb, 0);
+    for (int k = 1; k <= 6; k++) { tx = h_add(tx, h_mul(h_t[k - 1], xp[k])); txb = h_add(txb, h_mul(tb[k], xp[k])); }
+    sc eb = h_mul(x, h_add(ib, h_mul(x, h_add(ob, h_mul(x, sb)))));
+    append_scalar(t, "t_x", tx); append_scalar(t, "t_x_blinding", txb); append_scalar(t, "e_blinding", eb);
+    sc w = challenge_scalar(t, "w");
+
+    // ---- l(x), r(x) and the inner-product argument
+    sc h4[5] = {xp[1], xp[2], xp[3], u, w};
+    CUDA_TRY(cudaMemcpyAsync(d_small + 6, h4, sizeof h4, cudaMemcpyHostToDevice, s));
+    sc *d_a = (sc *)ctx->scratch[13].p, *d_b = d_a + N, *d_EG = d_b + N, *d_EH = d_EG + N;
+    k_poly_phase2<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)n, (uint32_t)N, d_small + 6, d_l1, d_aO, d_sL, d_r0, d_r1, d_r3, ty.lo, ty.hi, tyi.lo, tyi.hi, d_a,
+                                                d_b, d_EG, d_EH);
+    KCHECK();
+    t.append("dom-sep", (const uint8_t *)"ipp v1", 6);
+    t.append_u64("n", N);
+    sc *d_sG = (sc *)ctx->scratch[12].p, *d_sH = d_sG + N; // l1.. are dead now
+    std::vector<uint8_t> LR(64 * (lgN ? lgN : 1));
+    for (int j = 0; j < lgN; j++) {
+        uint32_t nj = (uint32_t)(N >> j), h = nj >> 1;
+        unsigned cb = (unsigned)std::min<size_t>((h + 127) / 128, 1184);
+        k_ipp_cross<<<cb, 128, 0, s>>>(h, d_a, d_b, d_parts);
+        KCHECK();
+        k_sum_partials<2><<<1, 128, 0, s>>>(d_parts, cb, d_small + 24);
+        KCHECK();
+        k_ipp_cw<<<1, 32, 0, s>>>(d_small + 24, d_small + 10, d_small + 13);
+        KCHECK();
+        k_ipp_expand<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)N, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
+        KCHECK();
+        memset(&plan, 0, sizeof plan);
+        plan.ngroups = 2;
+        add_seg(d_sG, N, 0, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h);                 // G_i: right half -> L (group 0)
+        add_seg(d_sH, N, (uint32_t)ctx->cap, 0); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // H_i: right half -> R (group 1)
+        add_seg(d_small + 13, 1, pB, 0);
+        add_seg(d_small + 14, 1, pB, 1);
+        CTX_TRY(msm_run(ctx, s, &plan, res));
+        CTX_TRY(run_compress(ctx, s, res, 2, d_enc));
+        CUDA_TRY(cudaMemcpyAsync(LR.data() + 64 * j, d_enc, 64, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        t.append("L", LR.data() + 64 * j, 32);
+        t.append("R", LR.data() + 64 * j + 32, 32);
+        sc uj = challenge_scalar(t, "u");
+        sc uu[2] = {uj, h_inv(uj)};
+        CUDA_TRY(cudaMemcpyAsync(d_small + 11, uu, sizeof uu, cudaMemcpyHostToDevice, s));
+        k_ipp_fold<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)N, nj, d_small + 11, d_a, d_b, d_EG, d_EH);
+        KCHECK();
+    }
+    sc fab[2];
+    CUDA_TRY(cudaMemcpyAsync(&fab[0], d_a, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&fab[1], d_b, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // ---- R1CSProof::to_bytes
+    uint8_t *o = proof;
+    if (legacy) { memcpy(o, AIe, 32); memcpy(o + 32, AOe, 32); memcpy(o + 64, Se, 32); memset(o + 96, 0, 96); o += 192; }
+    else { *o++ = 0; memcpy(o, AIe, 32); memcpy(o + 32, AOe, 32); memcpy(o + 64, Se, 32); o += 96; }
+    memcpy(o, Te, 160); o += 160;
+    sc_tobytes(o, tx); sc_tobytes(o + 32, txb); sc_tobytes(o + 64, eb); o += 96;
+    memcpy(o, LR.data(), 64 * (size_t)lgN); o += 64 * (size_t)lgN;
+    sc_tobytes(o, fab[0]); sc_tobytes(o + 32, fab[1]); o += 64;
+    return (long)(o - proof);
+}
+
+// ================================================================ Verifier::verify
+extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
+                               size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept) {
+    if (!ctx || !c || !label || !proof || !ext_rng32 || !accept) return BPG_E_ARG;
+    *accept = 0;
+    size_t n = c->n, m = c->m;
+    if (m && !V32) return BPG_E_ARG;
+    // ---- R1CSProof::from_bytes (FormatError -> reject)
+    const uint8_t *A[6];
+    uint8_t Z32[32] = {0};
+    const uint8_t *f;
+    size_t nf;
+    if (flags & BPG_FLAG_LEGACY_FRAMING) {
+        if (proof_len % 32 || proof_len < 14 * 32) return BPG_OK;
+        for (int i = 0; i < 6; i++) A[i] = proof + 32 * i;
+        f = proof + 192; nf = proof_len / 32 - 6;
+    } else {
+        if (proof_len == 0) return BPG_OK;
+        int ver = proof[0];
+        size_t body = proof_len - 1;
+        if (body % 32 || (ver != 0 && ver != 1)) return BPG_OK;
+        if (body < (size_t)(ver == 0 ? 11 : 14) * 32) return BPG_OK;
+        if (ver == 0) { for (int i = 0; i < 3; i++) { A[i] = proof + 1 + 32 * i; A[3 + i] = Z32; } f = proof + 97; nf = body / 32 - 3; }
+        else { for (int i = 0; i < 6; i++) A[i] = proof + 1 + 32 * i; f = proof + 193; nf = body / 32 - 6; }
+    }
+    if (nf < 10 || (nf - 10) % 2) return BPG_OK;
+    const uint8_t *Tp = f;
+    sc tx, txb, eb, ia, ibb;
+    if (!sc_canonical_bytes(tx, f + 160) || !sc_canonical_bytes(txb, f + 192) || !sc_canonical_bytes(eb, f + 224)) return BPG_OK;
+    size_t lg = (nf - 10) / 2;
+    if (lg >= 32) return BPG_OK;
+    const uint8_t *LR = f + 256;
+    if (!sc_canonical_bytes(ia, LR + 64 * lg) || !sc_canonical_bytes(ibb, LR + 64 * lg + 32)) return BPG_OK;
+
+    bpgh::Transcript t(label, label_len);
+    t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
+    for (size_t i = 0; i < m; i++) t.append("V", V32 + 32 * i, 32);
+    t.append_u64("m", m);
+    static const char *AL[6] = {"A_I1", "A_O1", "S1", "A_I2", "A_O2", "S2"};
+    for (int i = 0; i < 3; i++) if (!t.validate_and_append_point(AL[i], A[i])) return BPG_OK;
+    t.append("dom-sep", (const uint8_t *)"r1cs-1phase", 11);
+    size_t N = next_pow2(n);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->cap < N) return BPG_OK; // InvalidGeneratorsLength -> Err
+    for (int i = 3; i < 6; i++) t.append(AL[i], A[i], 32);
+    sc y = challenge_scalar(t, "y"), z = challenge_scalar(t, "z");
+    static const char *TL[5] = {"T_1", "T_3", "T_4", "T_5", "T_6"};
+    for (int k = 0; k < 5; k++) if (!t.validate_and_append_point(TL[k], Tp + 32 * k)) return BPG_OK;
+    sc u = challenge_scalar(t, "u"), x = challenge_scalar(t, "x");
+    append_scalar(t, "t_x", tx); append_scalar(t, "t_x_blinding", txb); append_scalar(t, "e_blinding", eb);
+    sc w = challenge_scalar(t, "w");
+    if (N != ((size_t)1 << lg)) return BPG_OK;
+    t.append("dom-sep", (const uint8_t *)"ipp v1", 6);
+    t.append_u64("n", N);
+    sc ch[32], usq[32], uisq[32], allinv = SC_ONE_H;
+    for (size_t j = 0; j < lg; j++) {
+        if (!t.validate_and_append_point("L", LR + 64 * j)) return BPG_OK;
+        if (!t.validate_and_append_point("R", LR + 64 * j + 32)) return BPG_OK;
+        ch[j] = challenge_scalar(t, "u");
+    }
+    { // batch inversion of the lg challenges
+        sc prod = SC_ONE_H, pre[33];
+        for (size_t j = 0; j < lg; j++) { pre[j] = prod; prod = h_mul(prod, ch[j]); }
+        sc inv = h_inv(prod);
+        allinv = inv;
+        for (size_t j = lg; j-- > 0;) { sc cj = h_mul(inv, pre[j]); inv = h_mul(inv, ch[j]); usq[j] = h_mul(ch[j], ch[j]); uisq[j] = h_mul(cj, cj); }
+    }
+    sc yinv = h_inv(y);
+    bpgh::TranscriptRng rng(t);
+    rng.finalize(ext_rng32);
+    sc r = rng_scalar(rng);
+
+    cudaStream_t s = ctx->stream;
+    CTX_TRY(ctx->scratch[9].ensure(256 * sizeof(sc)));
+    sc *d_small = (sc *)ctx->scratch[9].p;
+    sc hs[8 + 32];
+    hs[0] = z; hs[1] = yinv; hs[2] = allinv; hs[3] = x; hs[4] = ia; hs[5] = ibb; hs[6] = u;
+    for (size_t j = 0; j < lg; j++) hs[8 + j] = usq[j];
+    CUDA_TRY(cudaMemcpyAsync(d_small, hs, sizeof(sc) * (8 + lg), cudaMemcpyHostToDevice, s));
+    size_t ptz = pow_tab_size((uint32_t)c->q + 1), pty = pow_tab_size((uint32_t)N);
+    CTX_TRY(ctx->scratch[10].ensure((ptz + 2 * pty) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[11].ensure(((size_t)c->ncols + 1) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[12].ensure((2 * N + 8) * sizeof(sc)));
+    CTX_TRY(ctx->scratch[14].ensure(4096 * 6 * sizeof(sc)));
+    pow_tab tz, tyi, ts;
+    sc *d_pt = (sc *)ctx->scratch[10].p;
+    CTX_TRY(make_pow_tables(ctx, s, d_small + 0, (uint32_t)c->q + 1, d_pt, tz));
+    CTX_TRY(make_pow_tables(ctx, s, d_small + 1, (uint32_t)N, d_pt + ptz, tyi));
+    ts.lo = d_pt + ptz + pty; ts.hi = ts.lo + 1024;
+    uint32_t nshi = (uint32_t)(N >> 10) + 2;
+    k_s_tables<<<LAUNCH_1D(1024 + nshi, 128), 0, s>>>(d_small + 8, d_small + 2, (uint32_t)lg, ts.lo, ts.hi, nshi);
+    KCHECK();
+    sc *d_w = (sc *)ctx->scratch[11].p;
+    CTX_TRY(run_flatten(ctx, s, c, tz, d_w, ctx->scratch[15]));
+    sc *d_g = (sc *)ctx->scratch[12].p, *d_h = d_g + N, *d_parts = (sc *)ctx->scratch[14].p;
+    unsigned vb = (unsigned)std::min<size_t>((N + 127) / 128, 1184);
+    // vs = [x, a, b, u] at d_small + 3
+    k_verify_scalars<<<vb, 128, 0, s>>>((uint32_t)n, (uint32_t)N, d_small + 3, d_w, tyi.lo, tyi.hi, ts.lo, ts.hi, d_g, d_h, d_parts);
+    KCHECK();
+    k_sum_partials<1><<<1, 128, 0, s>>>(d_parts, vb, d_small + 48);
+    KCHECK();
+    sc delta, wc;
+    std::vector<sc> h_wV(m ? m : 1);
+    CUDA_TRY(cudaMemcpyAsync(&delta, d_small + 48, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&wc, d_w + 3 * n + m, 32, cudaMemcpyDeviceToHost, s));
+    if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // ---- scalars / points of the single verification MSM
+    sc xx = h_mul(x, x), xxx = h_mul(xx, x), rxx = h_mul(r, xx);
+    size_t k = 6 + m + 5 + 2 * lg;
+    std::vector<uint8_t> es(32 * k), ep(32 * k);
+    size_t ci = 0;
+    auto put = [&](const sc &sv, const uint8_t *pt) { sc_tobytes(es.data() + 32 * ci, sv); memcpy(ep.data() + 32 * ci, pt, 32); ci++; };
+    put(x, A[0]); put(xx, A[1]); put(xxx, A[2]); put(h_mul(u, x), A[3]); put(h_mul(u, xx), A[4]); put(h_mul(u, xxx), A[5]);
+    for (size_t j = 0; j < m; j++) put(h_mul(h_wV[j], rxx), V32 + 32 * j);
+    put(h_mul(r, x), Tp); put(h_mul(rxx, x), Tp + 32); put(h_mul(rxx, xx), Tp + 64); put(h_mul(rxx, xxx), Tp + 96); put(h_mul(h_mul(rxx, xx), xx), Tp + 128);
+    for (size_t j = 0; j < lg; j++) put(usq[j], LR + 64 * j);
+    for (size_t j = 0; j < lg; j++) put(uisq[j], LR + 64 * j + 32);
+    sc sB = h_add(h_mul(w, h_sub(tx, h_mul(ia, ibb))), h_mul(r, h_sub(h_mul(xx, h_add(wc, delta)), tx)));
+    sc sBb; sc_neg_r(sBb, h_add(eb, h_mul(r, txb)));
+    sc hb[2] = {sB, sBb};
+    CUDA_TRY(cudaMemcpyAsync(d_small + 50, hb, sizeof hb, cudaMemcpyHostToDevice, s));
+    CTX_TRY(ctx->scratch[2].ensure(64 * k + 64));
+    uint8_t *d_e = (uint8_t *)ctx->scratch[2].p;
+    CUDA_TRY(cudaMemcpyAsync(d_e, es.data(), 32 * k, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_e + 32 * k, ep.data(), 32 * k, cudaMemcpyHostToDevice, s));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    ge *res = (ge *)ctx->results.p;
+    uint32_t *d_ok = (uint32_t *)(res + 8);
+    uint32_t one = 1, ok = 1;
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
+    const uint32_t pB = (uint32_t)(2 * ctx->cap);
+    msm_plan plan;
+    memset(&plan, 0, sizeof plan);
+    plan.ngroups = 1;
+    auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0) {
+        msm_seg &sg = plan.seg[plan.nseg++];
+        sg.scalars = sp; sg.n = (uint32_t)cnt; sg.p0 = p0; sg.group = 0; sg.reduce = 0;
+    };
+    add_seg(d_g, N, 0); add_seg(d_h, N, (uint32_t)ctx->cap); add_seg(d_small + 50, 1, pB); add_seg(d_small + 51, 1, pB + 1);
+    CTX_TRY(msm_run(ctx, s, &plan, res));
+    CTX_TRY(varbase_msm_dev(ctx, s, d_e, d_e + 32 * k, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
+    k_points_sum_kernel<<<1, 64, 0, s>>>(res, 2, res + 2);
+    KCHECK();
+    uint8_t *d_enc = (uint8_t *)(res + 4), enc[32];
+    CTX_TRY(run_compress(ctx, s, res + 2, 1, d_enc));
+    CUDA_TRY(cudaMemcpyAsync(enc, d_enc, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    uint8_t nz = 0;
+    for (int i = 0; i < 32; i++) nz |= enc[i];
+    *accept = (ok && nz == 0) ? 1 : 0; // identity coset <=> all-zero encoding
+    return BPG_OK;
+}
