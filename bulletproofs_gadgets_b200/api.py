@@ -151,6 +151,25 @@ class Context:
     def launch_count(self):
         return self.lib.bpg_launch_count(self.h)
 
+    def event_record(self, slot):
+        self.check(self.lib.bpg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self.check(self.lib.bpg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def prof_enable(self, on=True):
+        self.check(self.lib.bpg_prof_enable(self.h, 1 if on else 0))
+
+    def prof_read(self):
+        n, ms, pairs = C.c_uint64(), C.c_double(), C.c_uint64()
+        self.check(self.lib.bpg_prof_read(self.h, C.byref(n), C.byref(ms), C.byref(pairs)))
+        return n.value, ms.value, pairs.value
+
+    def sync(self):
+        self.check(self.lib.bpg_sync(self.h))
+
     def bench_imad(self, iters):
         ms, mac = C.c_float(), C.c_double()
         self.check(self.lib.bpg_bench_imad(self.h, iters, C.byref(ms), C.byref(mac)))
@@ -246,7 +265,7 @@ class _ConstraintSystem:
     use (cs_buffer.rs:89-113): multiply, allocate, allocate_multiplier, constrain (+ the transcript label)."""
 
     def __init__(self, label, ctx, prover):
-        self.ctx = ctx or Context.default()
+        self._ctx = ctx  # resolved lazily: recording constraints needs no device
         self.label = bytes(label)
         self.is_prover = prover
         self.row_ptr, self.term_var, self.term_coeff = [0], [], bytearray()
@@ -254,6 +273,16 @@ class _ConstraintSystem:
         self.v, self.v_blinding, self.V = [], [], []
         self.num_vars = 0
         self._pending = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = Context.default()
+        return self._ctx
+
+    def csr(self):
+        """(row_ptr, term_var, term_coeff bytes) of the recorded constraints"""
+        return list(self.row_ptr), list(self.term_var), bytes(self.term_coeff)
 
     # -- evaluation of linear combinations over the prover's assignment (Prover::eval)
     def _eval(self, lc):

@@ -35,6 +35,9 @@ void dev_buf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 static int ensure_pinned(bpg_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_pinned_cap) return BPG_OK;
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->tev) if (e) cudaEventDestroy(e);
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0;
     CUDA_TRY(cudaMallocHost(&ctx->h_pinned, bytes + 4096));
     ctx->h_pinned_cap = bytes + 4096;
@@ -81,6 +84,9 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->tev) if (e) cudaEventDestroy(e);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -240,8 +246,18 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     if (total) {
         k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
         KCHECK();
+        bool prof = ctx->prof_on && ctx->prof_n < 4096;
+        if (prof) {
+            while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
+            CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s));
+        }
         k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p);
         KCHECK();
+        if (prof) {
+            CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], s));
+            CUDA_TRY(cudaMemcpyAsync(&ctx->prof_pairs[ctx->prof_n], offsets + nb, 4, cudaMemcpyDeviceToHost, s));
+            ctx->prof_n++;
+        }
     }
     k_msm_finish<<<LAUNCH_1D(nb, 128), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1);
     KCHECK();
@@ -422,6 +438,41 @@ extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t
     CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
+}
+
+extern "C" int bpg_event_record(bpg_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->tev[slot]) CUDA_TRY(cudaEventCreate(&ctx->tev[slot]));
+    CUDA_TRY(cudaEventRecord(ctx->tev[slot], ctx->stream));
+    return BPG_OK;
+}
+extern "C" int bpg_event_elapsed_ms(bpg_ctx *ctx, int a, int b, float *ms) {
+    if (!ctx || !ms || a < 0 || b < 0 || a >= 16 || b >= 16 || !ctx->tev[a] || !ctx->tev[b]) return BPG_E_ARG;
+    CUDA_TRY(cudaEventSynchronize(ctx->tev[b]));
+    CUDA_TRY(cudaEventElapsedTime(ms, ctx->tev[a], ctx->tev[b]));
+    return BPG_OK;
+}
+extern "C" int bpg_prof_enable(bpg_ctx *ctx, int on) {
+    if (!ctx) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (on && !ctx->prof_pairs) CUDA_TRY(cudaMallocHost((void **)&ctx->prof_pairs, 4096 * 4));
+    ctx->prof_on = on;
+    if (on) ctx->prof_n = 0;
+    return BPG_OK;
+}
+extern "C" int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *pairs_total) {
+    if (!ctx || !launches || !ms_total || !pairs_total) return BPG_E_ARG;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    double ms = 0; uint64_t pairs = 0;
+    for (size_t i = 0; i < ctx->prof_n; i++) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ms += t; pairs += ctx->prof_pairs[i];
+    }
+    *launches = ctx->prof_n; *ms_total = ms; *pairs_total = pairs;
+    return BPG_OK;
 }
 
 extern "C" int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32) {

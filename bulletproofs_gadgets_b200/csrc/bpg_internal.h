@@ -52,6 +52,11 @@ struct bpg_ctx {
     // generic scratch
     dev_buf scratch[16];
     void *h_pinned = nullptr; size_t h_pinned_cap = 0;
+    cudaEvent_t tev[16] = {nullptr};
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev; // pairs (start, stop) around k_msm_accumulate
+    uint32_t *prof_pairs = nullptr;   // pinned: pair count per profiled launch
+    size_t prof_n = 0;
     uint64_t launches = 0;    // kernels launched (reported by bench.py as gpu_launches)
     std::string last_error;
 };

@@ -219,9 +219,10 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     sc *d_aL = (sc *)ctx->scratch[8].p, *d_aR = d_aL + N, *d_aO = d_aR + N, *d_sL = d_aO + N, *d_sR = d_sL + N;
     sc *d_small = (sc *)ctx->scratch[9].p; // [0..2] blindings, [3] y, [4] z, [5] yinv, [6..9] x,x2,x3,u, [10] w, [11..12] u,uinv, [13..14] cL*w,cR*w, [16..] T scalars
     if (n) {
-        CUDA_TRY(cudaMemcpyAsync(d_aL, aL, 32 * n, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(d_aR, aR, 32 * n, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(d_aO, aO, 32 * n, cudaMemcpyHostToDevice, s));
+        cudaMemcpyKind wk = (flags & BPG_FLAG_WITNESS_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_TRY(cudaMemcpyAsync(d_aL, aL, 32 * n, wk, s));
+        CUDA_TRY(cudaMemcpyAsync(d_aR, aR, 32 * n, wk, s));
+        CUDA_TRY(cudaMemcpyAsync(d_aO, aO, 32 * n, wk, s));
         k_sc_reduce_inplace<<<LAUNCH_1D(3 * N, 256), 0, s>>>(d_aL, (uint32_t)(2 * N + n)); // aL|aR|aO regions (N-strided; padding is never read)
         KCHECK();
     }

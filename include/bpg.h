@@ -37,6 +37,7 @@ typedef struct bpg_circuit bpg_circuit;
 
 /* flags for bpg_r1cs_prove / bpg_r1cs_verify */
 #define BPG_FLAG_LEGACY_FRAMING 1u /* proof bytes without the 1-byte phase tag, 14 fixed fields */
+#define BPG_FLAG_WITNESS_ON_DEVICE 4u /* aL, aR, aO are device pointers to reduced scalars (HBM-resident timing) */
 #define BPG_FLAG_FAST_BLINDING 2u  /* s_L, s_R expanded on the device from a transcript-derived seed instead of
                                       2n sequential Merlin TranscriptRng draws: valid proofs, different bytes */
 
@@ -123,6 +124,15 @@ int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr);
 int bpg_dev_free(bpg_ctx *ctx, void *d_ptr);
 int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+/* timing on the library's own stream: record event slot i (0..15), elapsed milliseconds between two slots */
+int bpg_event_record(bpg_ctx *ctx, int slot);
+int bpg_event_elapsed_ms(bpg_ctx *ctx, int slot_a, int slot_b, float *ms);
+/* per-kernel profile of the MSM bucket-accumulation kernel (the dominant kernel): while enabled every launch is
+ * bracketed by CUDA events; bpg_prof_read returns the number of launches, their summed duration and the summed
+ * number of (term, window) pairs they accumulated since the last enable */
+int bpg_prof_enable(bpg_ctx *ctx, int on);
+int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *pairs_total);
 
 /* integer-pipe microbenchmark: runs `iters` dependent field multiplications per thread over a full-chip grid and
  * returns elapsed milliseconds (CUDA events) and the number of 32x32->64 multiply-accumulates executed */

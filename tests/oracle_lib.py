@@ -155,6 +155,15 @@ class Transcript:
 
 
 def _u32(a):
+    """ctypes uint32 array from a list or (zero-copy) from a numpy uint32 array"""
+    try:
+        import numpy as np
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, dtype=np.uint32)
+            _u32.keep = a
+            return a.ctypes.data_as(C.POINTER(C.c_uint32))
+    except ImportError:
+        pass
     return (C.c_uint32 * max(1, len(a)))(*a)
 
 
