@@ -219,7 +219,10 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     int G = plan->ngroups;
     uint32_t nb = (uint32_t)G * BPG_NBP;
     size_t maxpairs = (size_t)total * BPG_NWIN;
-    size_t nchunks = (maxpairs + BPG_CHUNK - 1) / BPG_CHUNK + 1;
+    // chunk = sorted pairs summed by one thread: sized so that the accumulate grid has >= ~8 warps per SM sub-partition
+    uint32_t CH = 8;
+    while (CH < BPG_CHUNK && maxpairs / CH > 160000) CH <<= 1;
+    size_t nchunks = (maxpairs + CH - 1) / CH + 1;
     CTX_TRY(ctx->counts.ensure((nb + 2) * 4));
     CTX_TRY(ctx->offsets.ensure((nb + 2) * 4));
     CTX_TRY(ctx->cursor.ensure((nb + 2) * 4));
@@ -227,9 +230,8 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     CTX_TRY(ctx->partial.ensure(2 * nchunks * sizeof(ge)));
     CTX_TRY(ctx->buckets.ensure((size_t)nb * sizeof(ge)));
     CTX_TRY(ctx->heavy.ensure((nb + 2) * 4));
-    size_t lvl = (BPG_NBP + 3) / 4 + 4;
-    CTX_TRY(ctx->lvlP.ensure(2 * (size_t)G * lvl * sizeof(ge)));
-    CTX_TRY(ctx->lvlQ.ensure(2 * (size_t)G * lvl * sizeof(ge)));
+    CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
+    CTX_TRY(ctx->lvlQ.ensure(2 * (size_t)G * sizeof(ge)));
     uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *heavy = (uint32_t *)ctx->heavy.p;
     CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 2) * 4, s));
@@ -251,7 +253,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
             while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
             CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s));
         }
-        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p);
+        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
         KCHECK();
         if (prof) {
             CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], s));
@@ -259,25 +261,19 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
             ctx->prof_n++;
         }
     }
-    k_msm_finish<<<LAUNCH_1D(nb, 128), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1);
+    k_msm_finish<<<LAUNCH_1D(nb, 128), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
     KCHECK();
     if (total) {
-        k_msm_heavy<<<64, 128, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1);
+        k_msm_heavy<<<64, 128, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
         KCHECK();
     }
-    // weighted sum: 32800 -> 8200 -> 2050 -> 513 -> (tail) 1
-    ge *PA = (ge *)ctx->lvlP.p, *PB = PA + (size_t)G * lvl, *QA = (ge *)ctx->lvlQ.p, *QB = QA + (size_t)G * lvl;
-    uint32_t n = BPG_NBP;
-    k_msm_wsum_level<<<dim3((n / 4 + 127) / 128, G), 128, 0, s>>>((const ge *)ctx->buckets.p, nullptr, n, BPG_NBP, PA, QA, (uint32_t)lvl);
+    // weighted sum over the 129 x 256 bucket matrix: row/column sums, small-weight multiples, combine
+    ge *rc = (ge *)ctx->lvlP.p, *out2 = (ge *)ctx->lvlQ.p;
+    k_msm_rowcol<<<dim3(BPG_NROWS + BPG_NCOLS, G), 128, 0, s>>>((const ge *)ctx->buckets.p, rc);
     KCHECK();
-    n = (n + 3) / 4;
-    k_msm_wsum_level<<<dim3((n / 4 + 128) / 128, G), 128, 0, s>>>(PA, QA, n, (uint32_t)lvl, PB, QB, (uint32_t)lvl);
+    k_msm_wfinal<<<dim3(2, G), 256, 0, s>>>(rc, out2);
     KCHECK();
-    n = (n + 3) / 4;
-    k_msm_wsum_level<<<dim3((n / 4 + 128) / 128, G), 128, 0, s>>>(PB, QB, n, (uint32_t)lvl, PA, QA, (uint32_t)lvl);
-    KCHECK();
-    n = (n + 3) / 4;
-    k_msm_wsum_tail<<<G, 128, 0, s>>>(PA, QA, n, (uint32_t)lvl, PB, QB, d_out);
+    k_msm_combine<<<1, 32, 0, s>>>(out2, (uint32_t)G, d_out);
     KCHECK();
     return BPG_OK;
 }

@@ -12,10 +12,10 @@
 #define BPG_WBITS 16                  // signed window width of the resident tables
 #define BPG_NWIN 16                   // floor(253/16)+1 windows
 #define BPG_NBW (1u << (BPG_WBITS - 1)) // |digit| in 1..32768
-#define BPG_NBP (BPG_NBW + 32u)       // buckets per group incl. unused bucket 0 and padding (multiple of 4)
+#define BPG_NBP (129u * 256u)          // buckets per group: index = |digit| in [0, 32768], padded to 129 rows x 256 columns
 #define BPG_MAX_GROUPS 4
 #define BPG_MAX_SEGS 12
-#define BPG_CHUNK 64                  // sorted pairs summed by one thread of the accumulate kernel
+#define BPG_CHUNK 64                  // max sorted pairs summed by one thread of the accumulate kernel (8..64, sized per MSM)
 #define BPG_HEAVY_SPAN 48             // buckets spanning more chunks than this go to the block-wide tree kernel
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bpg_set_cuda_error(e_, __FILE__, __LINE__); return BPG_E_CUDA; } } while (0)

@@ -179,6 +179,58 @@ BPG_HD void mul512(u32 *R, const u32 *a, const u32 *b) {
     for (int i = 0; i < 7; i++) R[9 + i] = t[i];
 }
 
+// same as mac4 but never reordered: used by the 4-way interleaved multiply below to force instruction-level parallelism
+BPG_HD void mac4v(u32 *acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(acc[8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+    mac4(acc, x0, x1, x2, x3, b);
+#endif
+}
+// NW independent 512-bit products with their carry chains interleaved row by row (2*NW independent chains in flight):
+// a single warp then runs close to the IMAD.WIDE issue rate instead of waiting on one carry chain at a time.
+template <int NW>
+BPG_HD void mul512_ilp(u32 (*R)[16], const u32 *const *a, const u32 *const *b) {
+    u32 E[NW][18], O[NW][18];
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+#pragma unroll
+        for (int i = 0; i < 18; i++) { E[k][i] = 0; O[k][i] = 0; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            if ((j & 1) == 0) {
+                mac4v(E[k] + j, a[k][0], a[k][2], a[k][4], a[k][6], b[k][j]);
+                mac4v(O[k] + j, a[k][1], a[k][3], a[k][5], a[k][7], b[k][j]);
+            } else {
+                mac4v(O[k] + j - 1, a[k][0], a[k][2], a[k][4], a[k][6], b[k][j]);
+                mac4v(E[k] + j + 1, a[k][1], a[k][3], a[k][5], a[k][7], b[k][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        R[k][0] = E[k][0];
+        u32 c = add8(R[k] + 1, E[k] + 1, O[k]);
+        u32 t[8];
+        (void)add8(t, E[k] + 9, O[k] + 8);
+        (void)addsmall8(t, c);
+#pragma unroll
+        for (int i = 0; i < 7; i++) R[k][9 + i] = t[i];
+    }
+}
 // ---------------------------------------------------------------- field
 // reduce a 512-bit product: 2^256 = 38 (mod p)
 BPG_HD void fe_reduce512(fe &r, const u32 *R) {
@@ -211,6 +263,14 @@ BPG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
     fe_reduce512(r, R);
 }
 BPG_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+// four independent field multiplications, interleaved (latency-bound kernels only: ~200 live registers)
+BPG_HD void fe_mul4(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1, fe &r2, const fe &a2, const fe &b2, fe &r3,
+                    const fe &a3, const fe &b3) {
+    u32 R[4][16];
+    const u32 *pa[4] = {a0.v, a1.v, a2.v, a3.v}, *pb[4] = {b0.v, b1.v, b2.v, b3.v};
+    mul512_ilp<4>(R, pa, pb);
+    fe_reduce512(r0, R[0]); fe_reduce512(r1, R[1]); fe_reduce512(r2, R[2]); fe_reduce512(r3, R[3]);
+}
 BPG_HD void fe_add(fe &r, const fe &a, const fe &b) {
     u32 c = add8(r.v, a.v, b.v);
     c = addsmall8(r.v, 38u & (0u - c));

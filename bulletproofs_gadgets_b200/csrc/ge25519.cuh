@@ -50,6 +50,26 @@ BPG_HD void ge_add_an(ge &r, const ge &p, const ge_an &q) {
     fe_sub(e, b, a); fe_sub(f, d, c); fe_add(g, d, c); fe_add(h, b, a);
     fe_mul(r.X, e, f); fe_mul(r.Y, g, h); fe_mul(r.Z, f, g); fe_mul(r.T, e, h);
 }
+// same addition with the two groups of four independent multiplications interleaved (see fe_mul4)
+BPG_HD void ge_add_pn_ilp(ge &r, const ge &p, const ge_pn &q) {
+    fe a, b, c, d, e, f, g, h, t0, t1;
+    fe_sub(t0, p.Y, p.X); fe_add(t1, p.Y, p.X);
+    fe_mul4(a, t0, q.YmX, b, t1, q.YpX, c, p.T, q.T2d, d, p.Z, q.Z);
+    fe_dbl(d, d);
+    fe_sub(e, b, a); fe_sub(f, d, c); fe_add(g, d, c); fe_add(h, b, a);
+    fe_mul4(r.X, e, f, r.Y, g, h, r.Z, f, g, r.T, e, h);
+}
+BPG_HD void ge_add_ilp(ge &r, const ge &p, const ge &q) { ge_pn c; ge_to_pn(c, q); ge_add_pn_ilp(r, p, c); }
+BPG_HD void ge_dbl_ilp(ge &r, const ge &p) {
+    fe a, b, c, d, e, f, g, h, t;
+    fe_add(t, p.X, p.Y);
+    fe_mul4(a, p.X, p.X, b, p.Y, p.Y, c, p.Z, p.Z, t, t, t);
+    fe_dbl(c, c);
+    fe_neg(d, a);
+    fe_sub(e, t, a); fe_sub(e, e, b);
+    fe_add(g, d, b); fe_sub(f, g, c); fe_sub(h, d, b);
+    fe_mul4(r.X, e, f, r.Y, g, h, r.Z, f, g, r.T, e, h);
+}
 BPG_HD void ge_add(ge &r, const ge &p, const ge &q) { ge_pn c; ge_to_pn(c, q); ge_add_pn(r, p, c); }
 BPG_HD void ge_sub(ge &r, const ge &p, const ge &q) { ge_pn c, n; ge_to_pn(c, q); ge_pn_neg(n, c); ge_add_pn(r, p, n); }
 // dbl-2008-hwcd, a = -1: 4M + 4S

@@ -18,7 +18,7 @@
 //                            else queued for 6
 //   6. k_msm_heavy           block-wide tree reduction for buckets split over many chunks (e.g. the bit-valued
 //                            a_L/a_R of range proofs put half of all terms in bucket 1)
-//   7. k_msm_wsum_level / k_msm_wsum_tail   log-depth evaluation of sum_b b * bucket[b]
+//   7. k_msm_rowcol / k_msm_wfinal / k_msm_combine   sum_b b * bucket[b] via row and column sums (depth ~40)
 #pragma once
 #include "kernels_core.cuh"
 
@@ -73,28 +73,52 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     }
 }
 
-// exclusive scan of counts[0..n) into offsets[0..n] and cursor[0..n) ; single block, n <= 4 * 32800
+// exclusive scan of counts[0..n) into offsets[0..n] and cursor[0..n); one block walks coalesced tiles of 1024
 __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t n, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
-    __shared__ uint32_t part[1024];
-    uint32_t t = threadIdx.x;
-    uint32_t per = (n + 1023u) / 1024u;
-    uint32_t lo = t * per, hi = min(n, lo + per);
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += counts[i];
-    part[t] = s;
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = t >= off ? part[t - off] : 0;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + t;
+        uint32_t v = i < n ? counts[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
         __syncthreads();
-        part[t] += v;
+        if (wid == 0) {
+            uint32_t w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + (wid ? wsum[wid - 1] : 0u) + x - v;
+        if (i < n) { offsets[i] = excl; cursor[i] = excl; }
+        __syncthreads();
+        if (t == 1023) carry_s = carry + wsum[31];
         __syncthreads();
     }
-    uint32_t run = t == 0 ? 0 : part[t - 1];
-    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; cursor[i] = run; run += counts[i]; }
-    if (t == 1023) offsets[n] = part[1023];
+    if (t == 0) offsets[n] = carry_s;
 }
 
+__device__ __forceinline__ void block_tree_sum_ilp(ge &acc, ge *smem, int nthreads) { // result in thread 0
+    int t = threadIdx.x;
+    st_ge(&smem[t], acc);
+    __syncthreads();
+    for (int s = nthreads >> 1; s > 0; s >>= 1) {
+        if (t < s) {
+            ge b;
+            ld_ge(b, &smem[t + s]);
+            ge_add_ilp(acc, acc, b);
+            st_ge(&smem[t], acc);
+        }
+        __syncthreads();
+    }
+}
 // value -> table entry (negated if the sign bit is set)
 __device__ __forceinline__ void msm_load_entry(ge_an &a, const ge_an *__restrict__ tab, uint32_t v) {
     ld_an(a, &tab[v & 0x7FFFFFFFu]);
@@ -106,12 +130,12 @@ __device__ __forceinline__ void msm_load_entry(ge_an &a, const ge_an *__restrict
 
 // partial slot layout: partial[2*chunk + 0] = run touching the chunk start, [2*chunk + 1] = run touching the chunk end only
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets, uint32_t nbuckets,
-                                                         const ge_an *__restrict__ tab, ge *__restrict__ buckets, ge *__restrict__ partial) {
+                                                         const ge_an *__restrict__ tab, ge *__restrict__ buckets, ge *__restrict__ partial, uint32_t CH) {
     uint32_t M = offsets[nbuckets];
     uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t start64 = (uint64_t)chunk * BPG_CHUNK;
+    uint64_t start64 = (uint64_t)chunk * CH;
     if (start64 >= M) return;
-    uint32_t start = (uint32_t)start64, end = min(M, start + BPG_CHUNK);
+    uint32_t start = (uint32_t)start64, end = min(M, start + CH);
     // bucket containing `start`: largest b with offsets[b] <= start
     uint32_t lo = 0, hi = nbuckets;
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= start) lo = mid; else hi = mid; }
@@ -150,98 +174,111 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restri
 }
 
 __global__ void __launch_bounds__(128) k_msm_finish(const uint32_t *__restrict__ offsets, uint32_t nbuckets, ge *__restrict__ buckets,
-                                                     const ge *__restrict__ partial, uint32_t *__restrict__ heavy_list, uint32_t *__restrict__ heavy_count) {
+                                                     const ge *__restrict__ partial, uint32_t *__restrict__ heavy_list, uint32_t *__restrict__ heavy_count,
+                                                     uint32_t CH) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbuckets) return;
     uint32_t s = offsets[b], e = offsets[b + 1];
     if (s == e) { ge id; ge_identity(id); st_ge(&buckets[b], id); return; }
-    uint32_t c0 = s / BPG_CHUNK, c1 = (e - 1) / BPG_CHUNK;
+    uint32_t c0 = s / CH, c1 = (e - 1) / CH;
     if (c0 == c1) return; // written by the accumulate kernel
     if (c1 - c0 + 1 > BPG_HEAVY_SPAN) { heavy_list[atomicAdd(heavy_count, 1u)] = b; return; }
     ge acc;
-    ld_ge(acc, &partial[2ull * c0 + ((s % BPG_CHUNK) == 0 ? 0 : 1)]);
+    ld_ge(acc, &partial[2ull * c0 + ((s % CH) == 0 ? 0 : 1)]);
 #pragma unroll 1
     for (uint32_t c = c0 + 1; c <= c1; c++) {
         ge q;
         ld_ge(q, &partial[2ull * c]);
-        ge_add(acc, acc, q);
+        ge_add_ilp(acc, acc, q);
     }
     st_ge(&buckets[b], acc);
 }
 // one block per heavy bucket: threads stride over its partial slots, then tree-reduce in shared memory
 __global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *__restrict__ offsets, ge *__restrict__ buckets, const ge *__restrict__ partial,
-                                                    const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count) {
+                                                    const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count, uint32_t CH) {
     __shared__ ge smem[128];
     uint32_t nh = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
         uint32_t s = offsets[b], e = offsets[b + 1];
-        uint32_t c0 = s / BPG_CHUNK, c1 = (e - 1) / BPG_CHUNK;
+        uint32_t c0 = s / CH, c1 = (e - 1) / CH;
         ge acc;
         ge_identity(acc);
         for (uint32_t c = c0 + threadIdx.x; c <= c1; c += blockDim.x) {
             ge q;
-            uint32_t slot = (c == c0 && (s % BPG_CHUNK) != 0) ? 1u : 0u;
+            uint32_t slot = (c == c0 && (s % CH) != 0) ? 1u : 0u;
             ld_ge(q, &partial[2ull * c + slot]);
-            ge_add(acc, acc, q);
+            ge_add_ilp(acc, acc, q);
         }
-        block_sum_points(acc, smem);
+        block_tree_sum_ilp(acc, smem, 128);
         if (threadIdx.x == 0) st_ge(&buckets[b], acc);
         __syncthreads();
     }
 }
 
-// ---- weighted bucket sum.  Items i in [0,n): contribution i*P_i + Q_i.  One thread folds 4 items:
-//      P'_s = 4 * sum_k P_{4s+k},   Q'_s = sum_k (k*P_{4s+k} + Q_{4s+k}).   grid.y = group.
-__device__ __forceinline__ void wsum_fold4(ge &Pn, ge &Qn, const ge *Pin, const ge *Qin, uint32_t n, uint32_t s) {
-    ge run, wacc, t;
-    uint32_t i3 = 4 * s + 3, i2 = 4 * s + 2, i1 = 4 * s + 1, i0 = 4 * s;
-    if (i3 < n) ld_ge(run, &Pin[i3]); else ge_identity(run);
-    wacc = run;
-    if (i2 < n) { ld_ge(t, &Pin[i2]); ge_add(run, run, t); }
-    ge_add(wacc, wacc, run);
-    if (i1 < n) { ld_ge(t, &Pin[i1]); ge_add(run, run, t); }
-    ge_add(wacc, wacc, run);
-    if (i0 < n) { ld_ge(t, &Pin[i0]); ge_add(run, run, t); }
-    if (Qin) {
+// ---- weighted bucket sum  S = sum_b b * bucket[b]  over b = 256 q + r  (q < 129, r < 256):
+//      S = sum_r r * C_r + 256 * sum_q q * R_q   with row sums R_q = sum_r bucket[256 q + r] and column sums C_r.
+// Depth ~40 point operations instead of one serial pass over 32 768 buckets; every level is a block-wide tree
+// whose additions interleave their independent field multiplications (ge_add_ilp) because these kernels run at
+// one or two warps per scheduler.
+#define BPG_NROWS 129u
+#define BPG_NCOLS 256u
+// grid (129 + 256, groups), 128 threads: rc[g][0..129) = row sums, rc[g][129..385) = column sums
+__global__ void __launch_bounds__(128) k_msm_rowcol(const ge *__restrict__ buckets, ge *__restrict__ rc) {
+    __shared__ ge smem[128];
+    uint32_t g = blockIdx.y, idx = blockIdx.x, t = threadIdx.x;
+    const ge *B = buckets + (size_t)g * BPG_NBP;
+    ge acc, o;
+    if (idx < BPG_NROWS) {
+        ld_ge(acc, &B[256u * idx + t]);
+        ld_ge(o, &B[256u * idx + 128u + t]);
+        ge_add_ilp(acc, acc, o);
+    } else {
+        uint32_t r = idx - BPG_NROWS;
+        ld_ge(acc, &B[256u * t + r]);
+        if (t == 0) { ld_ge(o, &B[256u * 128u + r]); ge_add_ilp(acc, acc, o); }
+    }
+    block_tree_sum_ilp(acc, smem, 128);
+    if (t == 0) st_ge(&rc[(size_t)g * (BPG_NROWS + BPG_NCOLS) + idx], acc);
+}
+// w * P for a small weight (<= 8 bits), double-and-add from the top bit
+__device__ __forceinline__ void ge_small_mul(ge &r, uint32_t w, const ge &p) {
+    ge acc;
+    ge_identity(acc);
+    if (w) {
+        int top = 31 - __clz(w);
+        acc = p;
 #pragma unroll 1
-        for (uint32_t k = 0; k < 4; k++)
-            if (4 * s + k < n) { ld_ge(t, &Qin[4 * s + k]); ge_add(wacc, wacc, t); }
-    }
-    ge_dbl(run, run);
-    ge_dbl(run, run);
-    Pn = run;
-    Qn = wacc;
-}
-__global__ void __launch_bounds__(128) k_msm_wsum_level(const ge *__restrict__ Pin, const ge *__restrict__ Qin, uint32_t n, uint32_t in_stride,
-                                                         ge *__restrict__ Pout, ge *__restrict__ Qout, uint32_t out_stride) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t nseg = (n + 3) / 4;
-    if (s >= nseg) return;
-    uint32_t g = blockIdx.y;
-    ge Pn, Qn;
-    wsum_fold4(Pn, Qn, Pin + (size_t)g * in_stride, Qin ? Qin + (size_t)g * in_stride : nullptr, n, s);
-    st_ge(&Pout[(size_t)g * out_stride + s], Pn);
-    st_ge(&Qout[(size_t)g * out_stride + s], Qn);
-}
-// finishes the recursion inside one block per group (n <= 512 items), result -> out[g]
-__global__ void __launch_bounds__(128) k_msm_wsum_tail(ge *__restrict__ P, ge *__restrict__ Q, uint32_t n, uint32_t stride, ge *__restrict__ P2,
-                                                        ge *__restrict__ Q2, ge *__restrict__ out) {
-    uint32_t g = blockIdx.x;
-    ge *Pin = P + (size_t)g * stride, *Qin = Q + (size_t)g * stride, *Pout = P2 + (size_t)g * stride, *Qout = Q2 + (size_t)g * stride;
-    while (true) {
-        uint32_t nseg = (n + 3) / 4;
-        for (uint32_t s = threadIdx.x; s < nseg; s += blockDim.x) {
-            ge Pn, Qn;
-            wsum_fold4(Pn, Qn, Pin, Qin, n, s);
-            st_ge(&Pout[s], Pn);
-            st_ge(&Qout[s], Qn);
+        for (int k = top - 1; k >= 0; k--) {
+            ge_dbl_ilp(acc, acc);
+            if ((w >> k) & 1u) ge_add_ilp(acc, acc, p);
         }
-        __syncthreads();
-        if (nseg == 1) break;
-        ge *tp = Pin; Pin = Pout; Pout = tp;
-        tp = Qin; Qin = Qout; Qout = tp;
-        n = nseg;
     }
-    if (threadIdx.x == 0) { ge r; ld_ge(r, &Qout[0]); st_ge(&out[g], r); }
+    r = acc;
+}
+// grid (2, groups), 256 threads: x = 0 -> sum_r r C_r ; x = 1 -> 256 * sum_q q R_q ; out2[g][x]
+__global__ void __launch_bounds__(256) k_msm_wfinal(const ge *__restrict__ rc, ge *__restrict__ out2) {
+    __shared__ ge smem[256];
+    uint32_t g = blockIdx.y, which = blockIdx.x, t = threadIdx.x;
+    const ge *base = rc + (size_t)g * (BPG_NROWS + BPG_NCOLS);
+    ge item, acc;
+    if (which == 0) { ld_ge(item, &base[BPG_NROWS + t]); ge_small_mul(acc, t, item); }
+    else if (t < BPG_NROWS) { ld_ge(item, &base[t]); ge_small_mul(acc, t, item); }
+    else ge_identity(acc);
+    block_tree_sum_ilp(acc, smem, 256);
+    if (t == 0) {
+        if (which == 1) {
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) ge_dbl_ilp(acc, acc);
+        }
+        st_ge(&out2[2 * (size_t)g + which], acc);
+    }
+}
+__global__ void k_msm_combine(const ge *__restrict__ in2, uint32_t groups, ge *__restrict__ out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    ge a, b;
+    ld_ge(a, &in2[2 * g]); ld_ge(b, &in2[2 * g + 1]);
+    ge_add_ilp(a, a, b);
+    st_ge(&out[g], a);
 }

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) k_sum_partials(const sc *__restrict__ par
 }
 
 // ---------------------------------------------------------------- flattened constraints (a4 / a8)
-// Entries are sorted by (virtual) column.  A virtual column is a run of <= 256 entries of one variable; it either
+// Entries are sorted by (virtual) column.  A virtual column is a run of <= 32 entries of one variable; it either
 // writes w[dst] directly or, for variables split over several virtual columns, a partial slot (dst | 1<<31).
 // value = sum_k z^(row_k+1) * coeff_k   (coefficients of V / One columns are stored negated).
 __global__ void __launch_bounds__(128) k_flatten_vcols(const uint32_t *__restrict__ vcol_ptr, const uint32_t *__restrict__ vcol_dst, uint32_t nv,

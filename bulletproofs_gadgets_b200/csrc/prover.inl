@@ -60,7 +60,7 @@ extern "C" int bpg_mimc_hash_batch(bpg_ctx *ctx, const uint8_t *data, const uint
 }
 
 // ================================================================ R1CS circuit (flattened-constraint matrix, column-major on the device)
-#define BPG_VCOL 256u
+#define BPG_VCOL 32u
 struct bpg_circuit {
     bpg_ctx *ctx;
     size_t n, m, q, T;

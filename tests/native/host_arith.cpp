@@ -31,5 +31,12 @@ int ht_point_mul_add(const uint8_t *k, const uint8_t *p32, const uint8_t *q32, u
     ge_an nn; ge_an_neg(nn, an); ge_add_an(r2, r2, nn); ge r3; ge_scalarmul(r3, s, p); ge_sub(r3, r3, r2); out[96] = (uint8_t)ge_is_identity_coset(r3);
     return 1;
 }
+// ILP variants must agree with the plain ones: out = (P + Q) via ge_add_ilp, out+32 = 2P via ge_dbl_ilp
+int ht_ilp(const uint8_t *p32, const uint8_t *q32, uint8_t *out) {
+    ge p, q, r; if (!ristretto_decode(p, p32) || !ristretto_decode(q, q32)) return 0;
+    ge_add_ilp(r, p, q); ristretto_encode(out, r);
+    ge_dbl_ilp(r, p); ristretto_encode(out + 32, r);
+    return 1;
+}
 void ht_from_uniform(const uint8_t *b64, uint8_t *out) { ge p; ge_from_uniform_bytes(p, b64); ristretto_encode(out, p); }
 }

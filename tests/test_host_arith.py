@@ -98,6 +98,9 @@ def test_group_ops_and_ristretto(ht):
         assert o128.raw[32:64] == pr.ristretto_encode(pr.pt_dbl(R))  # doubling
         assert o128.raw[64:96] == pr.ristretto_encode(R)          # affine-Niels add
         assert o128.raw[96] == 1                                   # negation + coset identity test
+        o64 = C.create_string_buffer(64)
+        assert ht.ht_ilp(pr.ristretto_encode(Pp), pr.ristretto_encode(Q), o64) == 1
+        assert o64.raw[:32] == pr.ristretto_encode(pr.pt_add(Pp, Q)) and o64.raw[32:] == pr.ristretto_encode(pr.pt_dbl(Pp))
         w = rnd.randbytes(64)
         ht.ht_from_uniform(w, o)
         assert o.raw == pr.ristretto_encode(pr.from_uniform_bytes(w))
