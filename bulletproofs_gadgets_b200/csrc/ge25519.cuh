@@ -59,6 +59,15 @@ BPG_HD void ge_add_pn_ilp(ge &r, const ge &p, const ge_pn &q) {
     fe_sub(e, b, a); fe_sub(f, d, c); fe_add(g, d, c); fe_add(h, b, a);
     fe_mul4(r.X, e, f, r.Y, g, h, r.Z, f, g, r.T, e, h);
 }
+// mixed addition with an affine-Niels operand: 3 + 4 interleaved multiplications
+BPG_HD void ge_add_an_ilp(ge &r, const ge &p, const ge_an &q) {
+    fe a, b, c, d, e, f, g, h, t0, t1;
+    fe_sub(t0, p.Y, p.X); fe_add(t1, p.Y, p.X);
+    fe_mul3(a, t0, q.ymx, b, t1, q.ypx, c, p.T, q.t2d);
+    fe_dbl(d, p.Z);
+    fe_sub(e, b, a); fe_sub(f, d, c); fe_add(g, d, c); fe_add(h, b, a);
+    fe_mul4(r.X, e, f, r.Y, g, h, r.Z, f, g, r.T, e, h);
+}
 BPG_HD void ge_add_ilp(ge &r, const ge &p, const ge &q) { ge_pn c; ge_to_pn(c, q); ge_add_pn_ilp(r, p, c); }
 BPG_HD void ge_dbl_ilp(ge &r, const ge &p) {
     fe a, b, c, d, e, f, g, h, t;

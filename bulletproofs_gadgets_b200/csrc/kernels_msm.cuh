@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restri
 #pragma unroll 1
     while (pos < end) {
         uint32_t stop = min(end, bend);
-        // prefetch the sorted values of this run piece in registers one ahead
+        // (measured: interleaved multiplies / a software-pipelined gather cost occupancy here and were slower)
         uint32_t v = sorted[pos];
 #pragma unroll 1
         while (pos < stop) {

@@ -27,7 +27,7 @@ int ht_point_mul_add(const uint8_t *k, const uint8_t *p32, const uint8_t *q32, u
     ge d; ge_dbl(d, r); ristretto_encode(out + 32, d);
     // affine-Niels path: normalise q, add as affine Niels
     fe zi, x, y; fe_invert(zi, q.Z); fe_mul(x, q.X, zi); fe_mul(y, q.Y, zi);
-    ge_an an; ge_affine_to_an(an, x, y); ge r2; ge_scalarmul(r2, s, p); ge_add_an(r2, r2, an); ristretto_encode(out + 64, r2);
+    ge_an an; ge_affine_to_an(an, x, y); ge r2; ge_scalarmul(r2, s, p); ge_add_an_ilp(r2, r2, an); ristretto_encode(out + 64, r2);
     ge_an nn; ge_an_neg(nn, an); ge_add_an(r2, r2, nn); ge r3; ge_scalarmul(r3, s, p); ge_sub(r3, r3, r2); out[96] = (uint8_t)ge_is_identity_coset(r3);
     return 1;
 }
