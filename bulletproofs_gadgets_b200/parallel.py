@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing for the two ways the hot path shards.  One process per GPU;
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) carries only tiny payloads: 128-byte partial points,
+1-byte verdicts, timing scalars.  There is no data-path collective inside a proof."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most one)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_items(items, rank, world):
+    """round-robin ownership of independent proofs / verifications: item k -> rank k mod world"""
+    return [(k, it) for k, it in enumerate(items) if k % world == rank]
+
+
+def allgather_bytes(payload, device=None):
+    """all-gather equal-length byte strings; returns the list ordered by rank"""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return [bytes(payload)]
+    t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+
+def msm_gens_sharded(ctx, d_sG, d_sH, n, device=None):
+    """One MSM  sum sG[i] G[i] + sH[i] H[i]  split by point range over the ranks of the default process group.
+    d_sG / d_sH are this rank's device pointers to its OWN slice (shard_range(n, rank, world)) of the scalar vectors.
+    Every rank returns the same 32-byte compressed result."""
+    import ctypes as C
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(n, rank, world)
+    part = ctx.msm_gens_partial_dev(d_sG, d_sH, hi - lo, lo)
+    parts = allgather_bytes(part, device)
+    return ctx.points_sum_compress(b"".join(parts))
+
+
+def gather_verdicts(local, n_total, device=None):
+    """local: list of (index, bool) owned by this rank -> full list of verdicts on every rank"""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    buf = bytearray(n_total)
+    for k, v in local:
+        buf[k] = 2 if v else 1
+    if world == 1:
+        return [b == 2 for b in buf]
+    outs = allgather_bytes(bytes(buf), device)
+    res = []
+    for k in range(n_total):
+        vals = {o[k] for o in outs} - {0}
+        assert len(vals) == 1, "item %d owned by %d ranks" % (k, len(vals))
+        res.append(vals.pop() == 2)
+    return res

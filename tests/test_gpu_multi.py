@@ -1,0 +1,64 @@
+"""Multi-GPU test (needs >= 2 CUDA devices; run with `gpurun --gpus 2`): one MSM split by point range over 2 ranks with
+NCCL all-gather of the 128-byte partial points, and rank-sharded verification verdicts."""
+import os
+import random
+import socket
+
+import pytest
+import torch
+
+import oracle_lib as ol
+from oracle import pyref as pr
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, sG, sH, want, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import bulletproofs_gadgets_b200 as bpg
+    from bulletproofs_gadgets_b200 import parallel
+    try:
+        ctx = bpg.Context(rank)
+        ctx.gens_ensure(4096)
+        lo, hi = parallel.shard_range(n, rank, world)
+        dG, dH = ctx.dev_alloc(32 * (hi - lo)), ctx.dev_alloc(32 * (hi - lo))
+        ctx.dev_upload(dG, sG[32 * lo:32 * hi])
+        ctx.dev_upload(dH, sH[32 * lo:32 * hi])
+        got = parallel.msm_gens_sharded(ctx, dG, dH, n, device="cuda:%d" % rank)
+        q.put((rank, got == want))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_msm_point_range_split_over_two_gpus():
+    import torch.multiprocessing as mp
+    rnd = random.Random(13)
+    n, world = 3001, 2
+    sG = b"".join(rnd.randrange(pr.L).to_bytes(32, "little") for _ in range(n))
+    sH = b"".join(rnd.randrange(pr.L).to_bytes(32, "little") for _ in range(n))
+    want = ol.msm_gens(sG, sH, n, 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, sG, sH, want, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
