@@ -266,6 +266,64 @@ def mimc_chain_instance(nblocks, seed=5, ctx=None, label=b"mimc_chain", trace_on
                 aO=t[:, 2, :].tobytes(), csr=csr.finish(), root=dval)
 
 
+def bounds_check_batch_instance(count, nbytes=8, seed=5, label=b"bounds_batch", lo=0, hi=None, values=None):
+    """BASELINE config 3: `count` BoundsCheck gadgets (min <= v <= max on `nbytes`-byte values) in ONE proof.
+    Wiring per value as in bounds_check_gadget.rs:23-49 + utils.rs:5-35: commitments (v, a = v - min, b = max - v),
+    constraint a + b - (max - min) = 0, and two range proofs of n = 8*nbytes bits (per bit: allocate_multiplier(1 - bit, bit),
+    o = 0, a_i + b_i - 1 = 0; finally x - sum b_i 2^i = 0).  count = 4096, nbytes = 8 gives n = 2^19 multipliers,
+    m = 12 288 commitments, q = 1 060 864 constraints, and a bit-valued (a_L, a_R) witness with a_O = 0."""
+    nb = 8 * nbytes
+    hi = (1 << nb) - 1 if hi is None else hi
+    rng = np.random.default_rng(seed)
+    if values is None:
+        values = [int.from_bytes(rng.bytes(nbytes), "little") % (hi - lo + 1) + lo for _ in range(count)]
+    m1 = L_ORDER - 1
+    # ---- template of one value: (kind, index, coeff) per term, rows lengths
+    kinds, idxs, coefs, lens = [], [], [], []
+
+    def row(terms):
+        for k, i, c in terms:
+            kinds.append(k); idxs.append(i); coefs.append(c % L_ORDER)
+        lens.append(len(terms))
+
+    row([(3, 1, 1), (3, 2, 1), (4, 0, -(hi - lo))])
+    for which in (0, 1):
+        j0 = which * nb
+        for i in range(nb):
+            row([(2, j0 + i, 1)])
+            row([(0, j0 + i, 1), (1, j0 + i, 1), (4, 0, m1)])
+        row([(3, 1 + which, 1)] + [(1, j0 + i, -(1 << i)) for i in range(nb)])
+    kinds = np.array(kinds, dtype=np.uint32)
+    idxs = np.array(idxs, dtype=np.uint32)
+    coef_b = np.frombuffer(b"".join(int(c).to_bytes(32, "little") for c in coefs), dtype=np.uint8).reshape(-1, 32)
+    lens = np.array(lens, dtype=np.uint32)
+    k = np.arange(count, dtype=np.uint32)[:, None]
+    add = np.where(kinds < 3, 2 * nb, np.where(kinds == 3, 3, 0)).astype(np.uint32)[None, :]
+    tv = ((kinds[None, :] << 29) | (idxs[None, :] + k * add)).astype(np.uint32).reshape(-1)
+    tc = np.tile(coef_b, (count, 1))
+    all_lens = np.tile(lens, count)
+    row_ptr = np.zeros(len(all_lens) + 1, dtype=np.uint32)
+    np.cumsum(all_lens, out=row_ptr[1:])
+    # ---- witness
+    vals, bits = [], np.zeros((count, 2 * nb), dtype=np.uint8)
+    for c, v in enumerate(values):
+        a, b = (v - lo) % L_ORDER, (hi - v) % L_ORDER
+        vals += [v % L_ORDER, a, b]
+        ab, bb = a.to_bytes(32, "little"), b.to_bytes(32, "little")  # range_proof reads the raw scalar bytes (utils.rs:12-18)
+        for i in range(nb):
+            bits[c, i] = (ab[i // 8] >> (i % 8)) & 1
+            bits[c, nb + i] = (bb[i // 8] >> (i % 8)) & 1
+    n = count * 2 * nb
+    aR = np.zeros((n, 32), dtype=np.uint8)
+    aR[:, 0] = bits.reshape(-1)
+    aL = np.zeros((n, 32), dtype=np.uint8)
+    aL[:, 0] = 1 - bits.reshape(-1)
+    aO = np.zeros((n, 32), dtype=np.uint8)
+    blinds = [int.from_bytes(rng.bytes(64), "little") % L_ORDER for _ in vals]
+    return dict(label=label, n=n, m=3 * count, vals=_enc(vals), blinds=_enc(blinds), aL=aL.tobytes(), aR=aR.tobytes(), aO=aO.tobytes(),
+                csr=(row_ptr, np.ascontiguousarray(tv), np.ascontiguousarray(tc)), values=values)
+
+
 class Circuit:
     """device-resident constraint matrix (bpg_circuit) built from numpy CSR arrays"""
 
