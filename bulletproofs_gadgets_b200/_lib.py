@@ -51,6 +51,7 @@ SYMBOLS = {
     "bpg_event_elapsed_ms": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_float)]),
     "bpg_prof_enable": (_i32, [_vp, _i32]),
     "bpg_prof_read": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "bpg_bench_latency": (_i32, [_vp, _i32, C.POINTER(C.c_double)]),
     "bpg_bench_imad": (_i32, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
 }
 

@@ -170,6 +170,12 @@ class Context:
     def sync(self):
         self.check(self.lib.bpg_sync(self.h))
 
+    def bench_latency(self, iters=200):
+        out = (C.c_double * 8)()
+        self.check(self.lib.bpg_bench_latency(self.h, iters, out))
+        names = ["fe_mul", "ge_add", "ge_add_ilp", "ge_dbl", "ge_dbl_ilp", "ge_madd", "ge_madd_ilp", "fe_mul4"]
+        return dict(zip(names, [round(x, 1) for x in out]))
+
     def bench_imad(self, iters):
         ms, mac = C.c_float(), C.c_double()
         self.check(self.lib.bpg_bench_imad(self.h, iters, C.byref(ms), C.byref(mac)))

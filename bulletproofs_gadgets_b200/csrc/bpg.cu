@@ -220,8 +220,10 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     uint32_t nb = (uint32_t)G * BPG_NBP;
     size_t maxpairs = (size_t)total * BPG_NWIN;
     // chunk = sorted pairs summed by one thread: sized so that the accumulate grid has >= ~8 warps per SM sub-partition
-    uint32_t CH = 8;
-    while (CH < BPG_CHUNK && maxpairs / CH > 160000) CH <<= 1;
+    // (two full waves of 4 blocks x 128 threads on 148 SMs = 151 552 threads)
+    uint32_t CH = (uint32_t)((maxpairs + 151551) / 151552);
+    if (CH < 8) CH = 8;
+    if (CH > BPG_CHUNK) CH = BPG_CHUNK;
     size_t nchunks = (maxpairs + CH - 1) / CH + 1;
     CTX_TRY(ctx->counts.ensure((nb + 2) * 4));
     CTX_TRY(ctx->offsets.ensure((nb + 2) * 4));
@@ -490,6 +492,22 @@ extern "C" int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32)
     CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *mac32 = (double)blocks * threads * (double)iters * 2.0 * 72.0; // 64 limb products + 8 fold-by-38 per field multiply
+    return BPG_OK;
+}
+
+extern "C" int bpg_bench_latency(bpg_ctx *ctx, int iters, double cycles_per_op[8]) {
+    if (!ctx || !cycles_per_op || iters <= 0) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->scratch[5].ensure(256));
+    unsigned long long *d = (unsigned long long *)ctx->scratch[5].p;
+    for (int mode = 0; mode < 8; mode++) {
+        k_bench_latency<<<1, 32, 0, ctx->stream>>>(mode, iters, d, (uint32_t *)(d + 16));
+        KCHECK();
+    }
+    unsigned long long h[8];
+    CUDA_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; i++) cycles_per_op[i] = (double)h[i] / iters;
     return BPG_OK;
 }
 

@@ -299,3 +299,31 @@ __global__ void __launch_bounds__(256) k_bench_fe_mul(uint32_t *out, int iters) 
     for (int i = 0; i < 8; i++) x ^= a.v[i] ^ b.v[i];
     if (x == 0x12345678u) out[t] = x; // keep the chain alive without a store on the common path
 }
+
+// single-warp latency of dependent point / field operations (cycles per operation), the figure that governs the
+// low-parallelism tail kernels.  mode: 0 fe_mul  1 ge_add  2 ge_add_ilp  3 ge_dbl  4 ge_dbl_ilp  5 ge_add_an  6 ge_add_an_ilp  7 fe_mul4 (per 4)
+__global__ void __launch_bounds__(32) k_bench_latency(int mode, int iters, unsigned long long *cycles, uint32_t *sink) {
+    ge p, q;
+    ge_identity(p); ge_identity(q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { p.X.v[i] = threadIdx.x * 2654435761u + i; p.T.v[i] = i * 977u + 5; q.Y.v[i] = threadIdx.x + 40503u * i; q.Z.v[i] = i + 3; }
+    ge_pn qp; ge_to_pn(qp, q);
+    ge_an qa; qa.ypx = q.X; qa.ymx = q.Y; qa.t2d = q.Z;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        if (mode == 0) fe_mul(p.X, p.X, q.Y);
+        else if (mode == 1) ge_add_pn(p, p, qp);
+        else if (mode == 2) ge_add_pn_ilp(p, p, qp);
+        else if (mode == 3) ge_dbl(p, p);
+        else if (mode == 4) ge_dbl_ilp(p, p);
+        else if (mode == 5) ge_add_an(p, p, qa);
+        else if (mode == 6) ge_add_an_ilp(p, p, qa);
+        else fe_mul4(p.X, p.X, q.Y, p.Y, p.Y, q.Z, p.Z, p.Z, q.Y, p.T, p.T, q.Z);
+    }
+    long long t1 = clock64();
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= p.X.v[i] ^ p.Y.v[i] ^ p.Z.v[i] ^ p.T.v[i];
+    if (threadIdx.x == 0) { cycles[mode] = (unsigned long long)(t1 - t0); sink[0] = x; }
+}

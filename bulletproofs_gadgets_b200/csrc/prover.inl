@@ -180,6 +180,20 @@ int run_flatten(bpg_ctx *ctx, cudaStream_t s, bpg_circuit *c, const pow_tab &z, 
 }
 } // namespace
 
+// optional phase trace (BPG_TRACE=1): wall-clock per phase of bpg_r1cs_prove, printed to stderr
+#include <chrono>
+struct phase_trace {
+    bool on; std::chrono::steady_clock::time_point t0; std::string out;
+    phase_trace() : on(getenv("BPG_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *name) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        char b[96]; snprintf(b, sizeof b, " %s=%.3f", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        out += b; t0 = t1;
+    }
+    ~phase_trace() { if (on) fprintf(stderr, "[bpg prove ms]%s\n", out.c_str()); }
+};
+
 // ================================================================ Prover::prove
 // Buffer map (ctx->scratch):  8: witness aL|aR|aO|sL|sR (5N)   9: small scalars   10: power tables   11: w (3n+m+1)
 //                            12: l1|r0|r1|r3 (4n) -> later sG|sH (2N)   13: a|b|EG|EH (4N)   14: partial sums   15: flatten partials
@@ -200,6 +214,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     cudaStream_t s = ctx->stream;
     const uint32_t pB = (uint32_t)(2 * ctx->cap), pBb = pB + 1;
 
+    phase_trace tr;
     bpgh::Transcript t(label, label_len);
     t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
     // ---- V_i = v_i B + blinding_i B~  (batched; Prover::commit appends each to the transcript)
@@ -212,6 +227,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     for (size_t i = 0; i < m; i++) rng.rekey_with_witness_bytes("v_blinding", v_blinding + 32 * i, 32);
     rng.finalize(ext_rng32);
     sc ib = rng_scalar(rng), ob = rng_scalar(rng), sb = rng_scalar(rng);
+    tr.mark("commitV");
 
     // ---- upload the witness, start A_I1 / A_O1 while the host draws s_L, s_R
     CTX_TRY(ctx->scratch[8].ensure((5 * N + 8) * sizeof(sc)));
@@ -243,6 +259,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     add_seg(d_aL, n, 0, 0); add_seg(d_aR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 0, 1, pBb, 0);
     add_seg(d_aO, n, 0, 1); add_seg(d_small + 1, 1, pBb, 1);
     CTX_TRY(msm_run(ctx, s, &plan, res));
+    tr.mark("launchAIAO");
     // s_L, s_R: 2n sequential TranscriptRng draws on the host (byte-exact with the reference) ...
     std::vector<sc> h_s(2 * n + 1);
     if (flags & BPG_FLAG_FAST_BLINDING) {
@@ -265,6 +282,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     } else {
         for (size_t i = 0; i < 2 * n; i++) h_s[i] = rng_scalar(rng);
     }
+    tr.mark("rng");
     if (n) {
         CUDA_TRY(cudaMemcpyAsync(d_sL, h_s.data(), 32 * n, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(d_sR, h_s.data() + n, 32 * n, cudaMemcpyHostToDevice, s));
@@ -277,6 +295,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     uint8_t AIe[32], AOe[32], Se[32], h_enc[96];
     CUDA_TRY(cudaMemcpyAsync(h_enc, d_enc, 96, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    tr.mark("commitMSMs");
     memcpy(AIe, h_enc, 32); memcpy(AOe, h_enc + 32, 32); memcpy(Se, h_enc + 64, 32);
     t.append("A_I1", AIe, 32); t.append("A_O1", AOe, 32); t.append("S1", Se, 32);
     t.append("dom-sep", (const uint8_t *)"r1cs-1phase", 11);
@@ -315,6 +334,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     }
     if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    tr.mark("flatten+poly1");
     sc tb[7];
     tb[1] = rng_scalar(rng); tb[3] = rng_scalar(rng); tb[4] = rng_scalar(rng); tb[5] = rng_scalar(rng); tb[6] = rng_scalar(rng);
     // T_1, T_3, T_4, T_5, T_6
@@ -345,6 +365,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     k_poly_phase2<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)n, (uint32_t)N, d_small + 6, d_l1, d_aO, d_sL, d_r0, d_r1, d_r3, ty.lo, ty.hi, tyi.lo, tyi.hi, d_a,
                                                 d_b, d_EG, d_EH);
     KCHECK();
+    tr.mark("T+poly2");
     t.append("dom-sep", (const uint8_t *)"ipp v1", 6);
     t.append_u64("n", N);
     sc *d_sG = (sc *)ctx->scratch[12].p, *d_sH = d_sG + N; // l1.. are dead now
@@ -378,6 +399,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         k_ipp_fold<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)N, nj, d_small + 11, d_a, d_b, d_EG, d_EH);
         KCHECK();
     }
+    tr.mark("ipp");
     sc fab[2];
     CUDA_TRY(cudaMemcpyAsync(&fab[0], d_a, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&fab[1], d_b, 32, cudaMemcpyDeviceToHost, s));

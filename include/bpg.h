@@ -138,6 +138,10 @@ int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *
  * returns elapsed milliseconds (CUDA events) and the number of 32x32->64 multiply-accumulates executed */
 int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32);
 
+/* single-warp latency (SM cycles per operation) of dependent operations: [0] fe_mul [1] ge_add [2] ge_add interleaved
+ * [3] ge_dbl [4] ge_dbl interleaved [5] mixed add [6] mixed add interleaved [7] four interleaved fe_mul */
+int bpg_bench_latency(bpg_ctx *ctx, int iters, double cycles_per_op[8]);
+
 #ifdef __cplusplus
 }
 #endif
