@@ -32,6 +32,18 @@ int dev_buf::ensure(size_t bytes) {
 }
 void dev_buf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
+// Wait for the context's stream.  With BPG_BLOCKING_SYNC=1 the host thread sleeps on an event created with
+// cudaEventBlockingSync instead of spinning, which leaves the core to the other provers' transcript RNG.
+static int g_blocking_sync = -1;
+int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s) {
+    if (g_blocking_sync < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); g_blocking_sync = (e && e[0] == '1') ? 1 : 0; }
+    if (!g_blocking_sync || s != ctx->stream) { CUDA_TRY(cudaStreamSynchronize(s)); return BPG_OK; }
+    CUDA_TRY(cudaEventRecord(ctx->ev, s));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev));
+    return BPG_OK;
+}
+#define SYNC_TRY(ctx, s) CTX_TRY(bpg_stream_sync(ctx, s))
+
 static int ensure_pinned(bpg_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_pinned_cap) return BPG_OK;
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -70,7 +82,7 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     ctx->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync));
     *out = ctx;
     return BPG_OK;
 }
@@ -94,20 +106,20 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
 }
 extern "C" const char *bpg_last_error(bpg_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_cuda_err.c_str(); }
 extern "C" uint64_t bpg_launch_count(bpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
-extern "C" int bpg_sync(bpg_ctx *ctx) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return BPG_OK; }
+extern "C" int bpg_sync(bpg_ctx *ctx) { if (!ctx) return BPG_E_ARG; SYNC_TRY(ctx, ctx->stream); return BPG_OK; }
 
 extern "C" int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr) { if (!ctx || !d_ptr) return BPG_E_ARG; CUDA_TRY(cudaSetDevice(ctx->device)); CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 1)); return BPG_OK; }
 extern "C" int bpg_dev_free(bpg_ctx *ctx, void *d_ptr) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaFree(d_ptr)); return BPG_OK; }
 extern "C" int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!ctx) return BPG_E_ARG;
     CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
 extern "C" int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return BPG_E_ARG;
     CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
 
@@ -153,7 +165,7 @@ extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
     KCHECK();
     k_build_comb<<<1, 64, 0, ctx->stream>>>(ctx->tab, ptotal, (uint32_t)(2 * cap), ctx->comb);
     KCHECK();
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     ctx->cap = cap;
     ctx->ptotal = ptotal;
     return BPG_OK;
@@ -172,7 +184,7 @@ extern "C" int bpg_gens_export(bpg_ctx *ctx, size_t i0, size_t n, uint8_t *G32, 
     KCHECK();
     if (G32) CUDA_TRY(cudaMemcpyAsync(G32, d, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (H32) CUDA_TRY(cudaMemcpyAsync(H32, d + 32 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
 extern "C" int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bb32[32]) {
@@ -184,7 +196,7 @@ extern "C" int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bb32[32]
     KCHECK();
     uint8_t h[64];
     CUDA_TRY(cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     if (B32) memcpy(B32, h, 32);
     if (Bb32) memcpy(Bb32, h + 32, 32);
     return BPG_OK;
@@ -193,7 +205,8 @@ extern "C" int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bb32[32]
 // ================================================================ device op wrappers
 static int run_compress(bpg_ctx *ctx, cudaStream_t s, const ge *d_pts, size_t n, uint8_t *d_out32) {
     if (!n) return BPG_OK;
-    k_compress_kernel<<<LAUNCH_1D(n, 128), 0, s>>>(d_pts, (uint32_t)n, d_out32);
+    if (n <= 32) k_compress_kernel<<<1, 32, 0, s>>>(d_pts, (uint32_t)n, d_out32);
+    else k_compress_kernel<<<LAUNCH_1D(n, 128), 0, s>>>(d_pts, (uint32_t)n, d_out32);
     KCHECK();
     return BPG_OK;
 }
@@ -225,7 +238,8 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     if (CH < 8) CH = 8;
     if (CH > BPG_CHUNK) CH = BPG_CHUNK;
     size_t nchunks = (maxpairs + CH - 1) / CH + 1;
-    CTX_TRY(ctx->counts.ensure((nb + 2) * 4));
+    uint32_t ntiles = (nb + 1023) / 1024;
+    CTX_TRY(ctx->counts.ensure((nb + 2 + ntiles + 2) * 4)); // counters, then the scan's ticket + per-tile totals
     CTX_TRY(ctx->offsets.ensure((nb + 2) * 4));
     CTX_TRY(ctx->cursor.ensure((nb + 2) * 4));
     CTX_TRY(ctx->sorted.ensure((maxpairs + 1) * 4));
@@ -233,10 +247,10 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     CTX_TRY(ctx->buckets.ensure((size_t)nb * sizeof(ge)));
     CTX_TRY(ctx->heavy.ensure((nb + 2) * 4));
     CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
-    CTX_TRY(ctx->lvlQ.ensure(2 * (size_t)G * sizeof(ge)));
+    CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
     uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *heavy = (uint32_t *)ctx->heavy.p;
-    CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 2) * 4, s));
+    CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 2 + ntiles + 2) * 4, s));
     CUDA_TRY(cudaMemsetAsync(heavy + nb + 1, 0, 4, s));
     msm_params P;
     memcpy(P.seg, plan->seg, sizeof(P.seg));
@@ -245,7 +259,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
         k_msm_digits<0><<<LAUNCH_1D(total, 256), 0, s>>>(P, counts, nullptr);
         KCHECK();
     }
-    k_msm_scan<<<1, 1024, 0, s>>>(counts, nb, offsets, cursor);
+    k_msm_scan<<<ntiles, 256, 0, s>>>(counts, nb, offsets, cursor, counts + nb + 2);
     KCHECK();
     if (total) {
         k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
@@ -263,19 +277,19 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
             ctx->prof_n++;
         }
     }
-    k_msm_finish<<<LAUNCH_1D(nb, 128), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
+    k_msm_finish<<<LAUNCH_1D(nb, 64), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
     KCHECK();
     if (total) {
-        k_msm_heavy<<<64, 128, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
+        k_msm_heavy<<<64, 64, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
         KCHECK();
     }
     // weighted sum over the 129 x 256 bucket matrix: row/column sums, small-weight multiples, combine
     ge *rc = (ge *)ctx->lvlP.p, *out2 = (ge *)ctx->lvlQ.p;
-    k_msm_rowcol<<<dim3(BPG_NROWS + BPG_NCOLS, G), 128, 0, s>>>((const ge *)ctx->buckets.p, rc);
+    k_msm_rowcol<<<dim3(BPG_NROWS + BPG_NCOLS, G), 64, 0, s>>>((const ge *)ctx->buckets.p, rc);
     KCHECK();
-    k_msm_wfinal<<<dim3(2, G), 256, 0, s>>>(rc, out2);
+    k_msm_wfinal<<<dim3(8, G), 64, 0, s>>>(rc, out2);
     KCHECK();
-    k_msm_combine<<<1, 32, 0, s>>>(out2, (uint32_t)G, d_out);
+    k_msm_combine<<<G, 32, 0, s>>>(out2, d_out);
     KCHECK();
     return BPG_OK;
 }
@@ -293,7 +307,7 @@ extern "C" int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t
     k_pedersen_kernel<<<LAUNCH_1D(n, 128), 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
     KCHECK();
     CUDA_TRY(cudaMemcpyAsync(out32, d + 64 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
 
@@ -359,7 +373,7 @@ static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const
     }
     if (out128) CUDA_TRY(cudaMemcpyAsync(out128, final_pt, 128, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
 extern "C" int bpg_msm_gens(bpg_ctx *ctx, const uint8_t *sG, const uint8_t *sH, size_t n, size_t offset, const uint8_t *extra_scalars,
@@ -386,7 +400,7 @@ extern "C" int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size
     KCHECK();
     CTX_TRY(run_compress(ctx, ctx->stream, res, 1, (uint8_t *)(res + 4)));
     CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
 extern "C" int bpg_msm(bpg_ctx *ctx, const uint8_t *scalars, const uint8_t *points32, size_t n, uint8_t out32[32]) {
@@ -407,7 +421,7 @@ extern "C" int bpg_msm(bpg_ctx *ctx, const uint8_t *scalars, const uint8_t *poin
     CTX_TRY(run_compress(ctx, s, res, 1, (uint8_t *)(res + 4)));
     CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
 extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t sr[32], const uint8_t *PL32, const uint8_t *PR32, size_t n, uint8_t *out32) {
@@ -434,7 +448,7 @@ extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t
     CTX_TRY(run_compress(ctx, s, pts + 2 * n, n, d + 64));
     CUDA_TRY(cudaMemcpyAsync(out32, d + 64, 32 * n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
 
@@ -454,7 +468,7 @@ extern "C" int bpg_event_elapsed_ms(bpg_ctx *ctx, int a, int b, float *ms) {
 extern "C" int bpg_prof_enable(bpg_ctx *ctx, int on) {
     if (!ctx) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     if (on && !ctx->prof_pairs) CUDA_TRY(cudaMallocHost((void **)&ctx->prof_pairs, 4096 * 4));
     ctx->prof_on = on;
     if (on) ctx->prof_n = 0;
@@ -462,7 +476,7 @@ extern "C" int bpg_prof_enable(bpg_ctx *ctx, int on) {
 }
 extern "C" int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *pairs_total) {
     if (!ctx || !launches || !ms_total || !pairs_total) return BPG_E_ARG;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     double ms = 0; uint64_t pairs = 0;
     for (size_t i = 0; i < ctx->prof_n; i++) {
         float t = 0;
@@ -506,7 +520,7 @@ extern "C" int bpg_bench_latency(bpg_ctx *ctx, int iters, double cycles_per_op[8
     }
     unsigned long long h[8];
     CUDA_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
     for (int i = 0; i < 8; i++) cycles_per_op[i] = (double)h[i] / iters;
     return BPG_OK;
 }

@@ -62,4 +62,5 @@ struct bpg_ctx {
 };
 
 // bpg.cu
+int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s);
 int msm_run(bpg_ctx *c, cudaStream_t s, msm_plan *plan, ge *d_out /* ngroups extended points */);

@@ -73,38 +73,58 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     }
 }
 
-// exclusive scan of counts[0..n) into offsets[0..n] and cursor[0..n); one block walks coalesced tiles of 1024
-__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t n, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_s;
+// Exclusive scan of counts[0..n) into offsets[0..n] and cursor[0..n).  Tiles of 1024 counters, one 256-thread block
+// each (small blocks so the scan can run in the register space left over by another context's accumulate grid).
+// A block publishes its tile total, then sums the totals of all earlier tiles (<= 128 values, one coalesced read);
+// tiles are claimed through a ticket so a block only ever waits for blocks that have already started.
+// state[0] = ticket, state[1 + i] = total of tile i | 0x80000000 once published (zeroed by the host before launch).
+__global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t n, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                                                   volatile uint32_t *state) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t s_tile, s_prefix;
     uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    if (t == 0) carry_s = 0;
+    if (t == 0) s_tile = atomicAdd((uint32_t *)&state[0], 1u);
     __syncthreads();
-    uint32_t vnext = t < n ? counts[t] : 0u;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        uint32_t i = base + t;
-        uint32_t v = vnext;
-        vnext = (i + 1024 < n) ? counts[i + 1024] : 0u; // prefetch the next tile behind this tile's barriers
-        uint32_t x = v;
+    uint32_t tile = s_tile;
+    uint32_t i0 = tile * 1024u + 4u * t;
+    uint32_t v[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wsum[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = wsum[lane];
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
+    uint32_t local = v[0] + v[1] + v[2] + v[3];
+    uint32_t x = local;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
-            wsum[lane] = w;
-        }
-        __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + (wid ? wsum[wid - 1] : 0u) + x - v;
-        if (i < n) { offsets[i] = excl; cursor[i] = excl; }
-        __syncthreads();
-        if (t == 1023) carry_s = carry + wsum[31];
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < 8 ? wsum[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
+        if (lane < 8) wsum[lane] = w;
+        if (lane == 7) { __threadfence(); state[1 + tile] = w | 0x80000000u; } // publish this tile's total
     }
-    if (t == 0) offsets[n] = carry_s;
+    __syncthreads();
+    // look back: sum of all earlier tiles' totals (each thread polls at most one predecessor)
+    uint32_t part = 0;
+    for (uint32_t p = t; p < tile; p += 256) {
+        uint32_t a;
+        do { a = state[1 + p]; } while (!(a & 0x80000000u));
+        part += a & 0x7FFFFFFFu;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
+    __shared__ uint32_t psum[8];
+    if (lane == 0) psum[wid] = part;
+    __syncthreads();
+    if (t == 0) { uint32_t pp = 0; for (int k = 0; k < 8; k++) pp += psum[k]; s_prefix = pp; }
+    __syncthreads();
+    uint32_t excl = s_prefix + (wid ? wsum[wid - 1] : 0u) + x - local;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i0 + k < n) { offsets[i0 + k] = excl; cursor[i0 + k] = excl; }
+        excl += v[k];
+    }
+    if (i0 <= n - 1 && n - 1 < i0 + 4) offsets[n] = excl; // the thread owning the last counter writes the grand total
 }
 
 __device__ __forceinline__ void block_tree_sum_ilp(ge &acc, ge *smem, int nthreads) { // result in thread 0
@@ -174,7 +194,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restri
     else st_ge(&partial[2ull * chunk + (run_start == start ? 0 : 1)], acc);
 }
 
-__global__ void __launch_bounds__(128) k_msm_finish(const uint32_t *__restrict__ offsets, uint32_t nbuckets, ge *__restrict__ buckets,
+__global__ void __launch_bounds__(64) k_msm_finish(const uint32_t *__restrict__ offsets, uint32_t nbuckets, ge *__restrict__ buckets,
                                                      const ge *__restrict__ partial, uint32_t *__restrict__ heavy_list, uint32_t *__restrict__ heavy_count,
                                                      uint32_t CH) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,9 +215,9 @@ __global__ void __launch_bounds__(128) k_msm_finish(const uint32_t *__restrict__
     st_ge(&buckets[b], acc);
 }
 // one block per heavy bucket: threads stride over its partial slots, then tree-reduce in shared memory
-__global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *__restrict__ offsets, ge *__restrict__ buckets, const ge *__restrict__ partial,
-                                                    const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count, uint32_t CH) {
-    __shared__ ge smem[128];
+__global__ void __launch_bounds__(64) k_msm_heavy(const uint32_t *__restrict__ offsets, ge *__restrict__ buckets, const ge *__restrict__ partial,
+                                                   const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count, uint32_t CH) {
+    __shared__ ge smem[64];
     uint32_t nh = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *__restrict__ 
             ld_ge(q, &partial[2ull * c + slot]);
             ge_add_ilp(acc, acc, q);
         }
-        block_tree_sum_ilp(acc, smem, 128);
+        block_tree_sum_ilp(acc, smem, 64);
         if (threadIdx.x == 0) st_ge(&buckets[b], acc);
         __syncthreads();
     }
@@ -224,22 +244,25 @@ __global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *__restrict__ 
 // one or two warps per scheduler.
 #define BPG_NROWS 129u
 #define BPG_NCOLS 256u
-// grid (129 + 256, groups), 128 threads: rc[g][0..129) = row sums, rc[g][129..385) = column sums
-__global__ void __launch_bounds__(128) k_msm_rowcol(const ge *__restrict__ buckets, ge *__restrict__ rc) {
-    __shared__ ge smem[128];
+// grid (129 + 256, groups), 64 threads: rc[g][0..129) = row sums, rc[g][129..385) = column sums
+// (64-thread blocks, like every tail kernel: <= 8 K registers per block, so they fit next to resident accumulate blocks)
+__global__ void __launch_bounds__(64) k_msm_rowcol(const ge *__restrict__ buckets, ge *__restrict__ rc) {
+    __shared__ ge smem[64];
     uint32_t g = blockIdx.y, idx = blockIdx.x, t = threadIdx.x;
     const ge *B = buckets + (size_t)g * BPG_NBP;
     ge acc, o;
     if (idx < BPG_NROWS) {
         ld_ge(acc, &B[256u * idx + t]);
-        ld_ge(o, &B[256u * idx + 128u + t]);
-        ge_add_ilp(acc, acc, o);
+#pragma unroll 1
+        for (uint32_t k = 1; k < 4; k++) { ld_ge(o, &B[256u * idx + 64u * k + t]); ge_add_ilp(acc, acc, o); }
     } else {
         uint32_t r = idx - BPG_NROWS;
         ld_ge(acc, &B[256u * t + r]);
+        ld_ge(o, &B[256u * (t + 64u) + r]);
+        ge_add_ilp(acc, acc, o);
         if (t == 0) { ld_ge(o, &B[256u * 128u + r]); ge_add_ilp(acc, acc, o); }
     }
-    block_tree_sum_ilp(acc, smem, 128);
+    block_tree_sum_ilp(acc, smem, 64);
     if (t == 0) st_ge(&rc[(size_t)g * (BPG_NROWS + BPG_NCOLS) + idx], acc);
 }
 // w * P for a small weight (<= 8 bits), double-and-add from the top bit
@@ -257,29 +280,41 @@ __device__ __forceinline__ void ge_small_mul(ge &r, uint32_t w, const ge &p) {
     }
     r = acc;
 }
-// grid (2, groups), 256 threads: x = 0 -> sum_r r C_r ; x = 1 -> 256 * sum_q q R_q ; out2[g][x]
-__global__ void __launch_bounds__(256) k_msm_wfinal(const ge *__restrict__ rc, ge *__restrict__ out2) {
-    __shared__ ge smem[256];
-    uint32_t g = blockIdx.y, which = blockIdx.x, t = threadIdx.x;
+// grid (8, groups), 64 threads.  Blocks 0..3: columns [64 x, 64 x + 64) -> sum r C_r ; blocks 4..7: rows [64 (x-4), ..) -> 256 sum q R_q
+// (rows exist for q < 129; the remaining threads contribute the identity).
+// out8[g][x] ; k_msm_combine adds the eight partial results of a group.
+__global__ void __launch_bounds__(64, 8) k_msm_wfinal(const ge *__restrict__ rc, ge *__restrict__ out8) {
+    __shared__ ge smem[64];
+    uint32_t g = blockIdx.y, x = blockIdx.x, t = threadIdx.x;
     const ge *base = rc + (size_t)g * (BPG_NROWS + BPG_NCOLS);
     ge item, acc;
-    if (which == 0) { ld_ge(item, &base[BPG_NROWS + t]); ge_small_mul(acc, t, item); }
-    else if (t < BPG_NROWS) { ld_ge(item, &base[t]); ge_small_mul(acc, t, item); }
-    else ge_identity(acc);
-    block_tree_sum_ilp(acc, smem, 256);
+    if (x < 4) {
+        uint32_t r = 64u * x + t;
+        ld_ge(item, &base[BPG_NROWS + r]);
+        ge_small_mul(acc, r, item);
+    } else {
+        uint32_t q = 64u * (x - 4) + t;
+        if (q < BPG_NROWS) { ld_ge(item, &base[q]); ge_small_mul(acc, q, item); } else ge_identity(acc);
+    }
+    block_tree_sum_ilp(acc, smem, 64);
     if (t == 0) {
-        if (which == 1) {
+        if (x >= 4) {
 #pragma unroll 1
             for (int k = 0; k < 8; k++) ge_dbl_ilp(acc, acc);
         }
-        st_ge(&out2[2 * (size_t)g + which], acc);
+        st_ge(&out8[8 * (size_t)g + x], acc);
     }
 }
-__global__ void k_msm_combine(const ge *__restrict__ in2, uint32_t groups, ge *__restrict__ out) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= groups) return;
-    ge a, b;
-    ld_ge(a, &in2[2 * g]); ld_ge(b, &in2[2 * g + 1]);
-    ge_add_ilp(a, a, b);
-    st_ge(&out[g], a);
+// one 32-thread block per group: sum of the 8 partial results
+__global__ void __launch_bounds__(32) k_msm_combine(const ge *__restrict__ in8, ge *__restrict__ out) {
+    __shared__ ge smem[8];
+    uint32_t g = blockIdx.x, t = threadIdx.x;
+    ge acc;
+    if (t < 8) { ld_ge(acc, &in8[8 * (size_t)g + t]); st_ge(&smem[t], acc); }
+    __syncwarp();
+    for (int s2 = 4; s2 > 0; s2 >>= 1) {
+        if (t < (uint32_t)s2) { ge b; ld_ge(b, &smem[t + s2]); ge_add_ilp(acc, acc, b); st_ge(&smem[t], acc); }
+        __syncwarp();
+    }
+    if (t == 0) st_ge(&out[g], acc);
 }

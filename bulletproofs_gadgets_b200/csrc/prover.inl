@@ -31,7 +31,7 @@ extern "C" int bpg_mimc_sponge_batch(bpg_ctx *ctx, const uint8_t *blocks, const 
     KCHECK();
     CUDA_TRY(cudaMemcpyAsync(out32, dout, 32 * n, cudaMemcpyDeviceToHost, s));
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, dout + 32 * n, tbytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     return BPG_OK;
 }
 // mimc_hash: be_to_scalars + pad (mimc.rs:61-97, conversions.rs:26-30) on the host, sponge on the device
@@ -294,7 +294,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CTX_TRY(run_compress(ctx, s, res, 3, d_enc));
     uint8_t AIe[32], AOe[32], Se[32], h_enc[96];
     CUDA_TRY(cudaMemcpyAsync(h_enc, d_enc, 96, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     tr.mark("commitMSMs");
     memcpy(AIe, h_enc, 32); memcpy(AOe, h_enc + 32, 32); memcpy(Se, h_enc + 64, 32);
     t.append("A_I1", AIe, 32); t.append("A_O1", AOe, 32); t.append("S1", Se, 32);
@@ -333,7 +333,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         CUDA_TRY(cudaMemcpyAsync(h_t, d_small + 16, sizeof h_t, cudaMemcpyDeviceToHost, s));
     }
     if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     tr.mark("flatten+poly1");
     sc tb[7];
     tb[1] = rng_scalar(rng); tb[3] = rng_scalar(rng); tb[4] = rng_scalar(rng); tb[5] = rng_scalar(rng); tb[6] = rng_scalar(rng);
@@ -390,7 +390,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         CTX_TRY(msm_run(ctx, s, &plan, res));
         CTX_TRY(run_compress(ctx, s, res, 2, d_enc));
         CUDA_TRY(cudaMemcpyAsync(LR.data() + 64 * j, d_enc, 64, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        SYNC_TRY(ctx, s);
         t.append("L", LR.data() + 64 * j, 32);
         t.append("R", LR.data() + 64 * j + 32, 32);
         sc uj = challenge_scalar(t, "u");
@@ -403,7 +403,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     sc fab[2];
     CUDA_TRY(cudaMemcpyAsync(&fab[0], d_a, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&fab[1], d_b, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
 
     // ---- R1CSProof::to_bytes
     uint8_t *o = proof;
@@ -522,7 +522,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CUDA_TRY(cudaMemcpyAsync(&delta, d_small + 48, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&wc, d_w + 3 * n + m, 32, cudaMemcpyDeviceToHost, s));
     if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
 
     // ---- scalars / points of the single verification MSM
     sc xx = h_mul(x, x), xxx = h_mul(xx, x), rxx = h_mul(r, xx);
@@ -565,7 +565,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CTX_TRY(run_compress(ctx, s, res + 2, 1, d_enc));
     CUDA_TRY(cudaMemcpyAsync(enc, d_enc, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    SYNC_TRY(ctx, s);
     uint8_t nz = 0;
     for (int i = 0; i < 32; i++) nz |= enc[i];
     *accept = (ok && nz == 0) ? 1 : 0; // identity coset <=> all-zero encoding
