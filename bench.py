@@ -247,6 +247,8 @@ def run_ours(args):
     ms_e2e, _ = timed(0, False, args.steps)
     ms_e2e = barrier_max(dist, local, ms_e2e)
     sampler.stop_flag = True
+    if rank == 0:
+        sampler.join(timeout=10)  # never leave a daemon thread (mid nvidia-smi call) running into interpreter shutdown
     nproofs = world * K * args.steps
 
     extras = {}

@@ -88,21 +88,34 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
 }
 extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     if (!ctx) return;
+    const bool dbg = getenv("BPG_TRACE_DESTROY") != nullptr;
+#define DSTEP(name) do { if (dbg) { fprintf(stderr, "[bpg destroy %p] %s\n", (void *)ctx, name); fflush(stderr); } } while (0)
+    DSTEP("begin");
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    DSTEP("synced");
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    DSTEP("prof events destroyed");
     if (ctx->tab) cudaFree(ctx->tab);
     if (ctx->comb) cudaFree(ctx->comb);
+    DSTEP("tables freed");
     dev_buf *bufs[] = {&ctx->counts, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->partial, &ctx->buckets, &ctx->lvlP, &ctx->lvlQ, &ctx->heavy, &ctx->results};
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
+    DSTEP("buffers freed");
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
-    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : ctx->tev) if (e) cudaEventDestroy(e);
+    DSTEP("pinned freed");
+    for (int i = 0; i < 16; i++) if (ctx->tev[i]) { if (dbg) fprintf(stderr, "[bpg destroy] tev[%d]=%p\n", i, (void *)ctx->tev[i]); cudaEventDestroy(ctx->tev[i]); }
+    DSTEP("timer events destroyed");
     if (ctx->ev) cudaEventDestroy(ctx->ev);
+    DSTEP("events destroyed");
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    DSTEP("streams destroyed");
     delete ctx;
+#undef DSTEP
 }
 extern "C" const char *bpg_last_error(bpg_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_cuda_err.c_str(); }
 extern "C" uint64_t bpg_launch_count(bpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -264,7 +277,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     if (total) {
         k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
         KCHECK();
-        bool prof = ctx->prof_on && ctx->prof_n < 4096;
+        bool prof = ctx->prof_on && ctx->prof_n < 64; // the first 64 launches after bpg_prof_enable are timed
         if (prof) {
             while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
             CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s));

@@ -129,7 +129,7 @@ int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
 int bpg_event_record(bpg_ctx *ctx, int slot);
 int bpg_event_elapsed_ms(bpg_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* per-kernel profile of the MSM bucket-accumulation kernel (the dominant kernel): while enabled every launch is
- * bracketed by CUDA events; bpg_prof_read returns the number of launches, their summed duration and the summed
+ * (up to the first 64 after enabling) is bracketed by CUDA events; bpg_prof_read returns the number of launches, their summed duration and the summed
  * number of (term, window) pairs they accumulated since the last enable */
 int bpg_prof_enable(bpg_ctx *ctx, int on);
 int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *pairs_total);
