@@ -334,3 +334,56 @@ __global__ void __launch_bounds__(128) k_verify_scalars(uint32_t n, uint32_t N, 
     block_sum_scalars<1>(&d, smem);
     if (threadIdx.x == 0) st_sc(&dparts[blockIdx.x], d);
 }
+
+// ---------------------------------------------------------------- BPG_FLAG_FAST_BLINDING: s_L, s_R on the device
+// out[i] = wide_reduce(Keccak-f[1600](seed || i || pad)[0..64)) : a transcript-seeded counter-mode expansion replacing the
+// 2n sequential Merlin TranscriptRng draws of the byte-exact mode (valid proofs, different bytes).
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+__device__ void keccak_f1600_dev(uint64_t *a) {
+    const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,
+                             0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL,
+                             0x0000000080008009ULL, 0x000000008000000AULL, 0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL,
+                             0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+                             0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+#pragma unroll 1
+    for (int rnd = 0; rnd < 24; rnd++) {
+        uint64_t c[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) {
+            uint64_t d = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+            for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
+        }
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+#pragma unroll
+            for (int y = 0; y < 5; y++) {
+                int src = x + 5 * y, dst = y + 5 * ((2 * x + 3 * y) % 5);
+                b[dst] = RHO[src] ? rotl64(a[src], RHO[src]) : a[src];
+            }
+#pragma unroll
+        for (int y = 0; y < 25; y += 5)
+#pragma unroll
+            for (int x = 0; x < 5; x++) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+        a[0] ^= RC[rnd];
+    }
+}
+__global__ void __launch_bounds__(128) k_expand_blinding(const uint64_t *__restrict__ seed4, uint32_t n, sc *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t st[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) st[k] = 0;
+    st[0] = seed4[0]; st[1] = seed4[1]; st[2] = seed4[2]; st[3] = seed4[3];
+    st[4] = i; st[5] = 0x1F; st[16] = 0x8000000000000000ULL;
+    keccak_f1600_dev(st);
+    u32 R[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { R[2 * k] = (u32)st[k]; R[2 * k + 1] = (u32)(st[k] >> 32); }
+    sc r;
+    sc_reduce512(r, R);
+    st_sc(&out[i], r);
+}

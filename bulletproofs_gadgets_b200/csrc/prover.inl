@@ -261,31 +261,27 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CTX_TRY(msm_run(ctx, s, &plan, res));
     tr.mark("launchAIAO");
     // s_L, s_R: 2n sequential TranscriptRng draws on the host (byte-exact with the reference) ...
-    std::vector<sc> h_s(2 * n + 1);
     if (flags & BPG_FLAG_FAST_BLINDING) {
-        // ... or a transcript-seeded counter-mode expansion (Keccak-f per element, 8 host threads): valid proofs, other bytes
-        uint8_t seed[32];
-        rng.fill_bytes(seed, 32);
-        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> th;
-        for (unsigned k = 0; k < nt; k++)
-            th.emplace_back([&, k] {
-                for (size_t i = k; i < 2 * n; i += nt) {
-                    uint64_t st[25] = {0};
-                    memcpy(st, seed, 32);
-                    st[4] = i; st[5] = 0x1F; st[16] = 0x8000000000000000ULL;
-                    bpgh::keccak_f1600(st);
-                    h_s[i] = h_wide((const uint8_t *)st);
-                }
-            });
-        for (auto &x : th) x.join();
+        // ... or a transcript-seeded counter-mode expansion on the device (one Keccak-f per element): valid proofs, other bytes
+        uint8_t seed[64]; // two independent 32-byte seeds: s_L, s_R
+        rng.fill_bytes(seed, 64);
+        CUDA_TRY(cudaMemcpyAsync(d_small + 60, seed, 64, cudaMemcpyHostToDevice, s));
+        if (n) {
+            k_expand_blinding<<<LAUNCH_1D(n, 128), 0, s>>>((const uint64_t *)(d_small + 60), (uint32_t)n, d_sL);
+            KCHECK();
+            k_expand_blinding<<<LAUNCH_1D(n, 128), 0, s>>>((const uint64_t *)(d_small + 61), (uint32_t)n, d_sR);
+            KCHECK();
+        }
+        tr.mark("rng(device)");
     } else {
+        std::vector<sc> h_s(2 * n + 1);
         for (size_t i = 0; i < 2 * n; i++) h_s[i] = rng_scalar(rng);
-    }
-    tr.mark("rng");
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(d_sL, h_s.data(), 32 * n, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(d_sR, h_s.data() + n, 32 * n, cudaMemcpyHostToDevice, s));
+        tr.mark("rng");
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(d_sL, h_s.data(), 32 * n, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_sR, h_s.data() + n, 32 * n, cudaMemcpyHostToDevice, s));
+            SYNC_TRY(ctx, s); // h_s is released at the end of this scope
+        }
     }
     memset(&plan, 0, sizeof plan);
     plan.ngroups = 1;
