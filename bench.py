@@ -278,8 +278,7 @@ def run_ours(args):
         for _ in range(args.steps):
             lanes[0].prove(ext, RES | bpg._lib.FLAG_FAST_BLINDING, True)
         extras["single_proof_latency_ms_fast_blinding"] = 1e3 * (time.perf_counter() - t0) / args.steps
-        ms_i, mac = ctx.bench_imad(400)
-        extras["imad"] = {"fe_mul_chain_mac32_per_s": mac / ms_i * 1e3}
+        extras["single_warp_latency_cycles"] = ctx.bench_latency(200)
         nh = 1 << 14
         leaves = [[os.urandom(32), os.urandom(32)] for _ in range(nh)]
         ctx.mimc_sponge_batch(leaves[:64])
@@ -308,6 +307,19 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved = (pairs * 100.0) / (kms * 1e-3) / 1e9 if kms > 0 else None
+        # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled to this run's pairs per launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_that_launch"] * (pairs / nl if nl else 0)
+        except Exception:
+            pass
+        # integer view of the same kernel: one mixed addition = 7 field multiplications = 504 32x32->64 multiply-accumulates;
+        # peak = the MAC32 rate a dependent fe_mul chain sustains at full occupancy on this GPU (bpg_bench_imad, measured below)
+        ms_i, mac = ctx.bench_imad(400)
+        imad_peak = mac / ms_i * 1e3
+        imad_ach = pairs * 504.0 / (kms * 1e-3) if kms > 0 else None
         line = {"metric": "r1cs_proofs_per_sec", "value": nproofs / (ms_value * 1e-3), "unit": "proofs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), Z_l)", "data": "synthetic",
@@ -321,10 +333,14 @@ def run_ours(args):
                 "proofs_per_sec_fast_blinding": nproofs / (ms_fast * 1e-3),
                 "host_cores": cores,
                 "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "launches": int(nl),
+                             "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "launches": int(nl),
+                             "algorithmic_bytes_per_launch": (pairs / nl * 100.0) if nl else None,
                              "avg_launch_ms": kms / nl if nl else None, "pairs_per_launch": pairs / nl if nl else None,
                              "note": "timed on lane 0 while the other provers share the GPU",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                "imad_roofline": {"kernel": "k_msm_accumulate", "achieved": imad_ach, "peak": imad_peak, "unit": "MAC32/s",
+                                  "frac": (imad_ach / imad_peak) if imad_ach else None,
+                                  "note": "the kernel is integer-multiply bound before it is HBM bound; peak = measured dependent fe_mul chain"},
                 "cpu_baseline": cpu, "clocks": sampler.summary()}
         line.update(extras)
         _emit(json.dumps(line))
