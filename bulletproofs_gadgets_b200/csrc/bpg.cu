@@ -83,6 +83,7 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming));
     *out = ctx;
     return BPG_OK;
 }
@@ -110,6 +111,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (int i = 0; i < 16; i++) if (ctx->tev[i]) { if (dbg) fprintf(stderr, "[bpg destroy] tev[%d]=%p\n", i, (void *)ctx->tev[i]); cudaEventDestroy(ctx->tev[i]); }
     DSTEP("timer events destroyed");
     if (ctx->ev) cudaEventDestroy(ctx->ev);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     DSTEP("events destroyed");
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

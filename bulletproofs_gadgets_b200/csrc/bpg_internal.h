@@ -41,7 +41,7 @@ struct dev_buf { // grow-only device buffer
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr, ev2 = nullptr;
     // resident generators
     size_t cap = 0;           // per-chain capacity (power of two); tables cover 2*cap+2 points
     uint32_t ptotal = 0;

@@ -535,15 +535,20 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     sc sBb; sc_neg_r(sBb, h_add(eb, h_mul(r, txb)));
     sc hb[2] = {sB, sBb};
     CUDA_TRY(cudaMemcpyAsync(d_small + 50, hb, sizeof hb, cudaMemcpyHostToDevice, s));
+    // The proof's own points (A_*, V_j, T_k, L_j, R_j) are decompressed and multiplied on the second stream while the
+    // fixed-base part over G, H, B, B~ runs on the first one.
+    cudaStream_t s2 = ctx->stream2;
     CTX_TRY(ctx->scratch[2].ensure(64 * k + 64));
     uint8_t *d_e = (uint8_t *)ctx->scratch[2].p;
-    CUDA_TRY(cudaMemcpyAsync(d_e, es.data(), 32 * k, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_e + 32 * k, ep.data(), 32 * k, cudaMemcpyHostToDevice, s));
     CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
     ge *res = (ge *)ctx->results.p;
     uint32_t *d_ok = (uint32_t *)(res + 8);
     uint32_t one = 1, ok = 1;
-    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_e, es.data(), 32 * k, cudaMemcpyHostToDevice, s2));
+    CUDA_TRY(cudaMemcpyAsync(d_e + 32 * k, ep.data(), 32 * k, cudaMemcpyHostToDevice, s2));
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s2));
+    CTX_TRY(varbase_msm_dev(ctx, s2, d_e, d_e + 32 * k, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
+    CUDA_TRY(cudaEventRecord(ctx->ev2, s2));
     const uint32_t pB = (uint32_t)(2 * ctx->cap);
     msm_plan plan;
     memset(&plan, 0, sizeof plan);
@@ -554,7 +559,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     };
     add_seg(d_g, N, 0); add_seg(d_h, N, (uint32_t)ctx->cap); add_seg(d_small + 50, 1, pB); add_seg(d_small + 51, 1, pB + 1);
     CTX_TRY(msm_run(ctx, s, &plan, res));
-    CTX_TRY(varbase_msm_dev(ctx, s, d_e, d_e + 32 * k, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
+    CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev2, 0));
     k_points_sum_kernel<<<1, 64, 0, s>>>(res, 2, res + 2);
     KCHECK();
     uint8_t *d_enc = (uint8_t *)(res + 4), enc[32];
