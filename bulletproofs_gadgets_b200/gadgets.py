@@ -63,6 +63,12 @@ def mimc_preprocess(witness_scalars):
     return [int.from_bytes(bytes([32]) * 32, "little") & ((1 << 255) - 1)]
 
 
+def mimc_preprocess_blocks(scalars):
+    """the padded block list mimc_hash absorbs (mimc.rs:61-97) for a preimage given as be_to_scalars(bytes)"""
+    d = mimc_preprocess(scalars)
+    return list(scalars[:-1]) + [d[0]] if len(d) == 2 else list(scalars) + [d[0]]
+
+
 # ----------------------------------------------------------------------------- reference-shaped wiring (generic, slow)
 def mimc_sponge_wire(cs, preimage_lcs):
     """MimcHash256::mimc_sponge over any ConstraintSystem mirror (Prover / Verifier of api.py)."""

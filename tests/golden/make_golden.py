@@ -41,7 +41,19 @@ def assignments(path):
     return d
 
 
+def copy_fixtures():
+    """the reference's CLI fixtures (data: .gadgets/.inst/.wtns triples of tests/resources and example.*) -> tests/golden/fixtures/"""
+    import shutil
+    dst = os.path.join(HERE, "fixtures")
+    os.makedirs(dst, exist_ok=True)
+    for f in sorted(os.listdir(os.path.join(REF, "tests", "resources"))):
+        shutil.copy(os.path.join(REF, "tests", "resources", f), os.path.join(dst, f))
+    for ext in (".gadgets", ".inst", ".wtns"):
+        shutil.copy(os.path.join(REF, "example" + ext), os.path.join(dst, "example" + ext))
+
+
 def main():
+    copy_fixtures()
     consts = byte_lists(read("src/mimc_hash/mimc_consts.rs"))
     assert len(consts) == 486 and all(len(c) == 32 for c in consts)
     with open(os.path.join(HERE, "mimc_consts.json"), "w") as f:
