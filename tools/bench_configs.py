@@ -31,7 +31,7 @@ def main():
     FAST, RES = bpg._lib.FLAG_FAST_BLINDING, bpg._lib.FLAG_WITNESS_ON_DEVICE
     ctx = bpg.Context(0)
     res = {}
-    which = sys.argv[1:] or ["3", "4", "5"]
+    which = sys.argv[1:] or ["0", "3", "4", "5"]
 
     def run(name, inst, cap):
         t_g, _ = timed(lambda: ctx.gens_ensure(cap))
@@ -50,6 +50,23 @@ def main():
                      "verify_ms": t_ver, "proof_bytes": len(proof), "verifier_accepts": bool(ok and ok_f), "tamper_rejected": rej}
         circ.close()
 
+    if "0" in which:
+        # config 0: the reference's own example.gadgets/.inst/.wtns through the front-end driver (prover + verifier binaries)
+        import tempfile, shutil
+        from bulletproofs_gadgets_b200 import frontend as fe
+        fx = os.path.join(ROOT, "tests", "golden", "fixtures")
+        d = tempfile.mkdtemp()
+        for ext in (".gadgets", ".inst", ".wtns"):
+            shutil.copy(os.path.join(fx, "example" + ext), os.path.join(d, "example" + ext))
+        stem = os.path.join(d, "example")
+        ctx.gens_ensure(1 << 14)
+        fe.prover_main(stem, seed=1, ctx=ctx, label="example")
+        t_p, nc = timed(lambda: fe.prover_main(stem, seed=1, ctx=ctx, label="example"), 2)
+        t_v, ok = timed(lambda: fe.verifier_main(stem, ctx=ctx, label="example"), 2)
+        run = fe.ProverRun(b"example", open(stem + ".gadgets").read(), open(stem + ".inst").read(), open(stem + ".wtns").read(), seed=1, ctx=ctx)
+        t_dev, _ = timed(lambda: run.prover.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32)), 2)
+        res["config0_example_cli"] = {"constraints": nc, "multipliers": run.prover.get_num_multiplications(), "prover_cli_ms_incl_python_frontend": t_p,
+                                      "verifier_cli_ms_incl_python_frontend": t_v, "prove_call_ms": t_dev, "verifier_prints": "true" if ok else "false"}
     if "3" in which:
         t0 = time.perf_counter()
         inst = gadgets.bounds_check_batch_instance(4096, 8, seed=5)
