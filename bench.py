@@ -195,7 +195,7 @@ def run_ours(args):
     if args.provers > 0:
         K = args.provers
     elif per_gpu >= 12:
-        K = 16                      # enough cores: one spinning host thread per prover
+        K = 16                      # enough cores: one spinning host thread per prover (24 sleeping provers measured no better)
     else:
         K = max(2, min(16, int(1.5 * per_gpu)))  # few cores per GPU (the byte-exact RNG is host-bound): oversubscribe, sleep in syncs
     if K * world > cores:
@@ -218,6 +218,9 @@ def run_ours(args):
         return outs
 
     def lane_run(ln, flags, resident, steps):
+        # staggered start (inside the timed region): lane i begins i * 3 ms late so that the lanes' host-RNG and device
+        # phases interleave from the first proof on instead of all lanes hitting the CPU, then the GPU, in lockstep
+        time.sleep(0.003 * lanes.index(ln))
         for _ in range(steps):
             ln.prove(ext, flags, resident)
 
