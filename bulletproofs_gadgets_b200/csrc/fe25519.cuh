@@ -231,6 +231,92 @@ BPG_HD void mul512_ilp(u32 (*R)[16], const u32 *const *a, const u32 *const *b) {
         for (int i = 0; i < 7; i++) R[k][9 + i] = t[i];
     }
 }
+
+// ---- squaring: 28 cross products (doubled by a 1-bit shift of the 512-bit partial) + 8 diagonal squares = 36 wide
+// multiplies instead of 64.  Cross products a_i a_j (i < j) are accumulated in the same even/odd carry-chain style as
+// mul512, with chains of 1..4 products.
+template <int K>
+BPG_HD void macK(u32 *acc, const u32 *x, u32 b) { // acc[0..2K-1] += {x[0], x[2], ..} * b at 64-bit slots ; acc[2K] += carry
+#ifdef __CUDA_ARCH__
+    if (K == 1) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(x[0]), "r"(b));
+    } else if (K == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(x[0]), "r"(x[2]), "r"(b));
+    } else if (K == 3) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\taddc.u32 %6, %6, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+            : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(b));
+    } else {
+        mac4(acc, x[0], x[2], x[4], x[6], b);
+    }
+#else
+    u64 c = 0;
+    for (int k = 0; k < K; k++) {
+        u64 p = (u64)x[2 * k] * b;
+        u64 t = (u64)acc[2 * k] + (u32)p + c;
+        acc[2 * k] = (u32)t; c = t >> 32;
+        t = (u64)acc[2 * k + 1] + (u32)(p >> 32) + c;
+        acc[2 * k + 1] = (u32)t; c = t >> 32;
+    }
+    acc[2 * K] += (u32)c;
+#endif
+}
+BPG_HD void sqr512(u32 *R, const u32 *a) {
+    // E: products whose word position i + j is even, O: odd positions (stored shifted down by one word)
+    u32 E[18], O[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
+    // row j multiplies a_j with the lower limbs a_i, i < j, split by the parity of i
+    // j = 1: i = 0           -> position 1 (odd)
+    macK<1>(O + 0, a + 0, a[1]);
+    // j = 2: i = 0 -> pos 2 (even) ; i = 1 -> pos 3 (odd)
+    macK<1>(E + 2, a + 0, a[2]);
+    macK<1>(O + 2, a + 1, a[2]);
+    // j = 3: i = 0, 2 -> pos 3, 5 (odd) ; i = 1 -> pos 4 (even)
+    macK<2>(O + 2, a + 0, a[3]);
+    macK<1>(E + 4, a + 1, a[3]);
+    // j = 4: i = 0, 2 -> pos 4, 6 (even) ; i = 1, 3 -> pos 5, 7 (odd)
+    macK<2>(E + 4, a + 0, a[4]);
+    macK<2>(O + 4, a + 1, a[4]);
+    // j = 5: i = 0, 2, 4 -> pos 5, 7, 9 (odd) ; i = 1, 3 -> pos 6, 8 (even)
+    macK<3>(O + 4, a + 0, a[5]);
+    macK<2>(E + 6, a + 1, a[5]);
+    // j = 6: i = 0, 2, 4 -> pos 6, 8, 10 (even) ; i = 1, 3, 5 -> pos 7, 9, 11 (odd)
+    macK<3>(E + 6, a + 0, a[6]);
+    macK<3>(O + 6, a + 1, a[6]);
+    // j = 7: i = 0, 2, 4, 6 -> pos 7, 9, 11, 13 (odd) ; i = 1, 3, 5 -> pos 8, 10, 12 (even)
+    macK<4>(O + 6, a + 0, a[7]);
+    macK<3>(E + 8, a + 1, a[7]);
+    // C = E + (O << 32)
+    u32 C[16];
+    C[0] = E[0];
+    u32 c = add8(C + 1, E + 1, O);
+    u32 t[8];
+    (void)add8(t, E + 9, O + 8);
+    (void)addsmall8(t, c);
+#pragma unroll
+    for (int i = 0; i < 7; i++) C[9 + i] = t[i];
+    // 2C (C < 2^511 because 2C <= a^2 < 2^512)
+    u32 D2[16];
+    D2[0] = C[0] << 1;
+#pragma unroll
+    for (int i = 1; i < 16; i++) D2[i] = (C[i] << 1) | (C[i - 1] >> 31);
+    // diagonal squares
+    u32 Dg[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u64 p = (u64)a[i] * a[i]; Dg[2 * i] = (u32)p; Dg[2 * i + 1] = (u32)(p >> 32); }
+    u32 c1 = add8(R, D2, Dg);
+    u32 hi[8];
+    (void)add8(hi, D2 + 8, Dg + 8);
+    (void)addsmall8(hi, c1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) R[8 + i] = hi[i];
+}
+
 // ---------------------------------------------------------------- field
 // reduce a 512-bit product: 2^256 = 38 (mod p)
 BPG_HD void fe_reduce512(fe &r, const u32 *R) {
@@ -262,7 +348,11 @@ BPG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
     mul512(R, a.v, b.v);
     fe_reduce512(r, R);
 }
-BPG_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+BPG_HD void fe_sqr(fe &r, const fe &a) {
+    u32 R[16];
+    sqr512(R, a.v);
+    fe_reduce512(r, R);
+}
 // four independent field multiplications, interleaved (latency-bound kernels only: ~200 live registers)
 BPG_HD void fe_mul4(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1, fe &r2, const fe &a2, const fe &b2, fe &r3,
                     const fe &a3, const fe &b3) {

@@ -12,6 +12,7 @@ void ht_consts(uint8_t *out7x32) {
 static void ldfe(fe &r, const uint8_t *b) { for (int i = 0; i < 8; i++) r.v[i] = (u32)b[4*i] | ((u32)b[4*i+1] << 8) | ((u32)b[4*i+2] << 16) | ((u32)b[4*i+3] << 24); }
 // raw 256-bit in, canonical out
 void ht_fe_mul(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe x, y, r; ldfe(x, a); ldfe(y, b); fe_mul(r, x, y); fe_tobytes(o, r); }
+void ht_fe_sqr(const uint8_t *a, uint8_t *o) { fe x, r; ldfe(x, a); fe_sqr(r, x); fe_tobytes(o, r); }
 void ht_fe_add(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe x, y, r; ldfe(x, a); ldfe(y, b); fe_add(r, x, y); fe_tobytes(o, r); }
 void ht_fe_sub(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe x, y, r; ldfe(x, a); ldfe(y, b); fe_sub(r, x, y); fe_tobytes(o, r); }
 void ht_fe_inv(const uint8_t *a, uint8_t *o) { fe x, r; ldfe(x, a); fe_invert(r, x); fe_tobytes(o, r); }

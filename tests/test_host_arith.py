@@ -54,6 +54,8 @@ def test_field_ops_weakly_reduced_inputs(ht):
         for y in (rnd.choice(vals), rnd.choice(edge), x):
             ht.ht_fe_mul(b(x), b(y), o)
             assert val(o) == x * y % P, (x, y)
+            ht.ht_fe_sqr(b(x), o)
+            assert val(o) == x * x % P, x
             ht.ht_fe_add(b(x), b(y), o)
             assert val(o) == (x + y) % P, (x, y)
             ht.ht_fe_sub(b(x), b(y), o)
