@@ -147,6 +147,24 @@ class Context:
         self.check(self.lib.bpg_mimc_sponge_batch(self.h, flat, (C.c_uint32 * (n + 1))(*offs), n, out, tr))
         return [out.raw[32 * i:32 * i + 32] for i in range(n)], (tr.raw if trace else None)
 
+    # ---- batch verification
+    def verify_batch(self, items, flags=0):
+        """items: list of (circuit handle (c_void_p), label bytes, V bytes, proof bytes, ext_rng32) -> list of bool,
+        verdict i being exactly what bpg_r1cs_verify returns for item i"""
+        n = len(items)
+        if n == 0:
+            return []
+        circs = (C.c_void_p * n)(*[it[0] for it in items])
+        labels = (C.c_char_p * n)(*[it[1] for it in items])
+        lens = (C.c_size_t * n)(*[len(it[1]) for it in items])
+        Vs = (C.c_char_p * n)(*[it[2] if it[2] else b"\0" for it in items])
+        proofs = (C.c_char_p * n)(*[it[3] if it[3] else b"\0" for it in items])
+        plens = (C.c_size_t * n)(*[len(it[3]) for it in items])
+        ext = b"".join(it[4] for it in items)
+        acc = (C.c_int * n)()
+        self.check(self.lib.bpg_r1cs_verify_batch(self.h, n, circs, labels, lens, Vs, proofs, plens, ext, flags, acc))
+        return [bool(a) for a in acc]
+
     # ---- misc
     def launch_count(self):
         return self.lib.bpg_launch_count(self.h)

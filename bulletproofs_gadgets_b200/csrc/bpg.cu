@@ -104,6 +104,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     dev_buf *bufs[] = {&ctx->counts, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->partial, &ctx->buckets, &ctx->lvlP, &ctx->lvlQ, &ctx->heavy, &ctx->results};
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
+    ctx->batch_gh.release();
     DSTEP("buffers freed");
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);

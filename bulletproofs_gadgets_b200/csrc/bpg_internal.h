@@ -51,6 +51,7 @@ struct bpg_ctx {
     dev_buf counts, offsets, cursor, sorted, partial, buckets, lvlP, lvlQ, heavy, results;
     // generic scratch
     dev_buf scratch[16];
+    dev_buf batch_gh;         // batch verification: every proof's g | h scalars
     void *h_pinned = nullptr; size_t h_pinned_cap = 0;
     cudaEvent_t tev[16] = {nullptr};
     int prof_on = 0;

@@ -387,3 +387,13 @@ __global__ void __launch_bounds__(128) k_expand_blinding(const uint64_t *__restr
     sc_reduce512(r, R);
     st_sc(&out[i], r);
 }
+
+// batch verification: Gacc[i] += rho * g[i], Hacc[i] += rho * h[i]  (scalars of proof i folded into the combined check)
+__global__ void __launch_bounds__(128) k_axpy_gh(sc rho, const sc *__restrict__ g, const sc *__restrict__ h, uint32_t n, sc *__restrict__ Gacc,
+                                                  sc *__restrict__ Hacc) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc a, x, p;
+    ld_sc(x, &g[i]); ld_sc(a, &Gacc[i]); sc_mul(p, rho, x); sc_add_r(a, a, p); st_sc(&Gacc[i], a);
+    ld_sc(x, &h[i]); ld_sc(a, &Hacc[i]); sc_mul(p, rho, x); sc_add_r(a, a, p); st_sc(&Hacc[i], a);
+}

@@ -413,10 +413,20 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
 }
 
 // ================================================================ Verifier::verify
-extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
-                               size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept) {
-    if (!ctx || !c || !label || !proof || !ext_rng32 || !accept) return BPG_E_ARG;
-    *accept = 0;
+// Stage 1 (per proof): R1CSProof::from_bytes, transcript replay, device-side scalar preparation.  Leaves the G/H scalars
+// g_i, h_i of the verification equation on the device (d_gh if given, else a scratch buffer) and the scalars / encodings
+// of the proof's own points, B and B~ on the host.  status = 0: the proof is rejected already (format / transcript).
+struct vprep {
+    int status = 0;
+    size_t N = 0, k = 0;
+    sc sB, sBb;
+    std::vector<uint8_t> es, ep; // k scalars, k compressed points
+    sc *d_g = nullptr, *d_h = nullptr;
+};
+static int verify_prepare(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
+                          size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, vprep &out, sc *d_gh) {
+    if (!ctx || !c || !label || !proof || !ext_rng32) return BPG_E_ARG;
+    out.status = 0;
     size_t n = c->n, m = c->m;
     if (m && !V32) return BPG_E_ARG;
     // ---- R1CSProof::from_bytes (FormatError -> reject)
@@ -494,7 +504,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     size_t ptz = pow_tab_size((uint32_t)c->q + 1), pty = pow_tab_size((uint32_t)N);
     CTX_TRY(ctx->scratch[10].ensure((ptz + 2 * pty) * sizeof(sc)));
     CTX_TRY(ctx->scratch[11].ensure(((size_t)c->ncols + 1) * sizeof(sc)));
-    CTX_TRY(ctx->scratch[12].ensure((2 * N + 8) * sizeof(sc)));
+    if (!d_gh) { CTX_TRY(ctx->scratch[12].ensure((2 * N + 8) * sizeof(sc))); d_gh = (sc *)ctx->scratch[12].p; }
     CTX_TRY(ctx->scratch[14].ensure(4096 * 6 * sizeof(sc)));
     pow_tab tz, tyi, ts;
     sc *d_pt = (sc *)ctx->scratch[10].p;
@@ -506,7 +516,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     KCHECK();
     sc *d_w = (sc *)ctx->scratch[11].p;
     CTX_TRY(run_flatten(ctx, s, c, tz, d_w, ctx->scratch[15]));
-    sc *d_g = (sc *)ctx->scratch[12].p, *d_h = d_g + N, *d_parts = (sc *)ctx->scratch[14].p;
+    sc *d_g = d_gh, *d_h = d_g + N, *d_parts = (sc *)ctx->scratch[14].p;
     unsigned vb = (unsigned)std::min<size_t>((N + 127) / 128, 1184);
     // vs = [x, a, b, u] at d_small + 3
     k_verify_scalars<<<vb, 128, 0, s>>>((uint32_t)n, (uint32_t)N, d_small + 3, d_w, tyi.lo, tyi.hi, ts.lo, ts.hi, d_g, d_h, d_parts);
@@ -533,11 +543,56 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     for (size_t j = 0; j < lg; j++) put(uisq[j], LR + 64 * j + 32);
     sc sB = h_add(h_mul(w, h_sub(tx, h_mul(ia, ibb))), h_mul(r, h_sub(h_mul(xx, h_add(wc, delta)), tx)));
     sc sBb; sc_neg_r(sBb, h_add(eb, h_mul(r, txb)));
+    out.sB = sB; out.sBb = sBb;
+    out.es.swap(es); out.ep.swap(ep);
+    out.N = N; out.k = k; out.d_g = d_g; out.d_h = d_h;
+    out.status = 1;
+    return BPG_OK;
+}
+
+// Stage 2: one check  sum_i rho_i * (verification equation of proof i) == identity  over a set of prepared proofs.
+// One proof with rho = 1 is exactly Verifier::verify's single multiscalar multiplication.  The fixed-base part runs on the
+// resident tables (scalars of all proofs are accumulated per generator first), the proofs' own points are decompressed
+// and multiplied on the second stream.
+static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std::vector<sc> &rho, int *pass) {
+    *pass = 0;
+    cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+    size_t Nmax = 0, ktot = 0;
+    for (vprep *p : S) { Nmax = std::max(Nmax, p->N); ktot += p->k; }
+    bool single = S.size() == 1 && rho[0].v[0] == 1 && !(rho[0].v[1] | rho[0].v[2] | rho[0].v[3] | rho[0].v[4] | rho[0].v[5] | rho[0].v[6] | rho[0].v[7]);
+    CTX_TRY(ctx->scratch[9].ensure(256 * sizeof(sc)));
+    sc *d_small = (sc *)ctx->scratch[9].p;
+    const sc *d_g, *d_h;
+    sc sB, sBb;
+    sc_set_u32(sB, 0); sc_set_u32(sBb, 0);
+    std::vector<uint8_t> es(32 * ktot), ep(32 * ktot);
+    size_t off = 0;
+    if (single) {
+        d_g = S[0]->d_g; d_h = S[0]->d_h;
+        sB = S[0]->sB; sBb = S[0]->sBb;
+        memcpy(es.data(), S[0]->es.data(), 32 * ktot); memcpy(ep.data(), S[0]->ep.data(), 32 * ktot);
+    } else {
+        CTX_TRY(ctx->scratch[13].ensure((2 * Nmax + 8) * sizeof(sc)));
+        sc *acc = (sc *)ctx->scratch[13].p;
+        CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * Nmax * sizeof(sc), s));
+        for (size_t i = 0; i < S.size(); i++) {
+            vprep *p = S[i];
+            k_axpy_gh<<<LAUNCH_1D(p->N, 128), 0, s>>>(rho[i], p->d_g, p->d_h, (uint32_t)p->N, acc, acc + Nmax);
+            KCHECK();
+            sB = h_add(sB, h_mul(rho[i], p->sB));
+            sBb = h_add(sBb, h_mul(rho[i], p->sBb));
+            for (size_t j = 0; j < p->k; j++) {
+                sc v; sc_frombytes(v, p->es.data() + 32 * j);
+                sc_tobytes(es.data() + 32 * (off + j), h_mul(rho[i], v));
+            }
+            memcpy(ep.data() + 32 * off, p->ep.data(), 32 * p->k);
+            off += p->k;
+        }
+        d_g = acc; d_h = acc + Nmax;
+    }
+    size_t k = ktot, N = Nmax;
     sc hb[2] = {sB, sBb};
     CUDA_TRY(cudaMemcpyAsync(d_small + 50, hb, sizeof hb, cudaMemcpyHostToDevice, s));
-    // The proof's own points (A_*, V_j, T_k, L_j, R_j) are decompressed and multiplied on the second stream while the
-    // fixed-base part over G, H, B, B~ runs on the first one.
-    cudaStream_t s2 = ctx->stream2;
     CTX_TRY(ctx->scratch[2].ensure(64 * k + 64));
     uint8_t *d_e = (uint8_t *)ctx->scratch[2].p;
     CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
@@ -569,6 +624,89 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     SYNC_TRY(ctx, s);
     uint8_t nz = 0;
     for (int i = 0; i < 32; i++) nz |= enc[i];
-    *accept = (ok && nz == 0) ? 1 : 0; // identity coset <=> all-zero encoding
+    *pass = (ok && nz == 0) ? 1 : 0; // identity coset <=> all-zero encoding
     return BPG_OK;
+}
+
+extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
+                               size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept) {
+    if (!accept) return BPG_E_ARG;
+    *accept = 0;
+    if (c && c->m && !V32) return BPG_E_ARG;
+    vprep p;
+    CTX_TRY(verify_prepare(ctx, c, label, label_len, V32, proof, proof_len, ext_rng32, flags, p, nullptr));
+    if (!p.status) return BPG_OK;
+    std::vector<vprep *> S = {&p};
+    std::vector<sc> rho = {SC_ONE_H};
+    return verify_finish(ctx, S, rho, accept);
+}
+
+// Batch verification: accept[i] is what bpg_r1cs_verify would return for proof i.  All proofs are prepared,
+// then ONE combined check with random weights rho_i (derived from every ext_rng32) decides the whole batch; if it fails,
+// the set is bisected until the failing proofs are isolated (a single proof is checked with rho = 1, i.e. exactly as by
+// bpg_r1cs_verify), so verdicts are identical to one-by-one verification up to the 2^-250 soundness error of the weights.
+static int verify_bisect(bpg_ctx *ctx, std::vector<vprep> &preps, const std::vector<sc> &rhos, const std::vector<size_t> &idx, size_t lo, size_t hi,
+                         bool known_bad, int *accept) {
+    if (lo >= hi) return BPG_OK;
+    int pass = 0;
+    if (!known_bad || hi - lo == 1) {
+        std::vector<vprep *> S;
+        std::vector<sc> rho;
+        for (size_t t = lo; t < hi; t++) { S.push_back(&preps[idx[t]]); rho.push_back(hi - lo == 1 ? SC_ONE_H : rhos[idx[t]]); }
+        CTX_TRY(verify_finish(ctx, S, rho, &pass));
+        if (pass) { for (size_t t = lo; t < hi; t++) accept[idx[t]] = 1; return BPG_OK; }
+        if (hi - lo == 1) { accept[idx[lo]] = 0; return BPG_OK; }
+    }
+    size_t mid = lo + (hi - lo) / 2;
+    // the set [lo, hi) is known to fail: check the left half; if it passes, the right half must contain the failure
+    std::vector<vprep *> S;
+    std::vector<sc> rho;
+    for (size_t t = lo; t < mid; t++) { S.push_back(&preps[idx[t]]); rho.push_back(mid - lo == 1 ? SC_ONE_H : rhos[idx[t]]); }
+    CTX_TRY(verify_finish(ctx, S, rho, &pass));
+    if (pass) {
+        for (size_t t = lo; t < mid; t++) accept[idx[t]] = 1;
+        return verify_bisect(ctx, preps, rhos, idx, mid, hi, true, accept);
+    }
+    if (mid - lo == 1) accept[idx[lo]] = 0;
+    else CTX_TRY(verify_bisect(ctx, preps, rhos, idx, lo, mid, true, accept));
+    return verify_bisect(ctx, preps, rhos, idx, mid, hi, false, accept);
+}
+
+extern "C" int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *const *circuits, const uint8_t *const *labels, const size_t *label_lens,
+                                     const uint8_t *const *V32, const uint8_t *const *proofs, const size_t *proof_lens, const uint8_t *ext_rng32,
+                                     unsigned flags, int *accept) {
+    if (!ctx || (count && (!circuits || !labels || !label_lens || !V32 || !proofs || !proof_lens || !ext_rng32 || !accept))) return BPG_E_ARG;
+    if (!count) return BPG_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < count; i++) {
+        accept[i] = 0;
+        if (!circuits[i] || !labels[i] || !proofs[i] || (circuits[i]->m && !V32[i])) return BPG_E_ARG;
+    }
+    // device storage for every proof's g_i | h_i
+    size_t total = 0;
+    std::vector<size_t> goff(count);
+    for (size_t i = 0; i < count; i++) { goff[i] = total; total += 2 * next_pow2(circuits[i]->n) + 8; }
+    CTX_TRY(ctx->batch_gh.ensure(total * sizeof(sc)));
+    sc *d_all = (sc *)ctx->batch_gh.p;
+    std::vector<vprep> preps(count);
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < count; i++) {
+        CTX_TRY(verify_prepare(ctx, circuits[i], labels[i], label_lens[i], V32[i], proofs[i], proof_lens[i], ext_rng32 + 32 * i, flags, preps[i], d_all + goff[i]));
+        if (preps[i].status) idx.push_back(i);
+    }
+    // weights: rho_i = wide_reduce(SHAKE256("bpg batch" || all ext_rng32 || i))  -- unpredictable to the provers
+    std::vector<sc> rhos(count);
+    for (size_t i : idx) {
+        bpgh::Sponge sp(136);
+        sp.absorb((const uint8_t *)"bpg batch", 9);
+        sp.absorb(ext_rng32, 32 * count);
+        uint8_t ib[8];
+        for (int b = 0; b < 8; b++) ib[b] = (uint8_t)((uint64_t)i >> (8 * b));
+        sp.absorb(ib, 8);
+        sp.finish(0x1F);
+        uint8_t w[64];
+        sp.squeeze(w, 64);
+        rhos[i] = h_wide(w);
+    }
+    return verify_bisect(ctx, preps, rhos, idx, 0, idx.size(), false, accept);
 }

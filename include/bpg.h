@@ -112,6 +112,14 @@ long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t l
 int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32,
                     const uint8_t *proof, size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept);
 
+/* Batch verification: accept[i] = what bpg_r1cs_verify returns for proof i.  The proofs are combined
+ * with random weights into ONE fixed-base multiscalar multiplication over the resident generators plus one
+ * variable-base launch over all proofs' own points; a failing combination is bisected until the invalid proofs are
+ * isolated, so verdicts equal one-by-one verification.  ext_rng32 = count x 32 bytes (one thread_rng stand-in per proof). */
+int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *const *circuits, const uint8_t *const *labels,
+                          const size_t *label_lens, const uint8_t *const *V32, const uint8_t *const *proofs,
+                          const size_t *proof_lens, const uint8_t *ext_rng32, unsigned flags, int *accept);
+
 /* Merlin transcript (host; sequential Keccak, never on the device) exposed for the Rust shim and the tests */
 typedef struct bpg_transcript bpg_transcript;
 bpg_transcript *bpg_transcript_new(const uint8_t *label, size_t len);
