@@ -3,6 +3,7 @@
 #include "bpg_internal.h"
 #include "consts.h"
 #include "host_merlin.h"
+#include "host_scalar64.h"
 #include "kernels_core.cuh"
 #include "kernels_msm.cuh"
 #include "kernels_vec.cuh"

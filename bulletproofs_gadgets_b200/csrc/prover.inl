@@ -140,15 +140,11 @@ extern "C" void bpg_circuit_destroy(bpg_circuit *c) {
 // ================================================================ host scalar helpers
 namespace {
 const sc SC_ONE_H = {{1, 0, 0, 0, 0, 0, 0, 0}};
-inline sc h_mul(const sc &a, const sc &b) { sc r; sc_mul(r, a, b); return r; }
+inline sc h_mul(const sc &a, const sc &b) { return bpgh::sc_mul64(a, b); }
 inline sc h_add(const sc &a, const sc &b) { sc r; sc_add_r(r, a, b); return r; }
 inline sc h_sub(const sc &a, const sc &b) { sc r; sc_sub_r(r, a, b); return r; }
-inline sc h_inv(const sc &a) { sc r; sc_invert(r, a); return r; }
-inline sc h_wide(const uint8_t b[64]) {
-    u32 R[16];
-    for (int i = 0; i < 16; i++) R[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
-    sc r; sc_reduce512(r, R); return r;
-}
+inline sc h_inv(const sc &a) { return bpgh::sc_invert64(a); }
+inline sc h_wide(const uint8_t b[64]) { return bpgh::sc_wide64(b); }
 inline sc challenge_scalar(bpgh::Transcript &t, const char *label) { uint8_t b[64]; t.challenge(label, b, 64); return h_wide(b); }
 inline sc rng_scalar(bpgh::TranscriptRng &rng) { uint8_t b[64]; rng.fill_bytes(b, 64); return h_wide(b); }
 inline void append_scalar(bpgh::Transcript &t, const char *label, const sc &x) { uint8_t b[32]; sc_tobytes(b, x); t.append(label, b, 32); }
@@ -422,16 +418,22 @@ struct vprep {
     sc sB, sBb;
     std::vector<uint8_t> es, ep; // k scalars, k compressed points
     sc *d_g = nullptr, *d_h = nullptr;
+    // state carried from the enqueue half to the completion half (after the device results have been read back)
+    size_t n = 0, m = 0, lg = 0;
+    sc x, u, r, w, tx, txb, eb, ia, ibb, usq[32], uisq[32];
+    const uint8_t *A[6] = {nullptr}, *Tp = nullptr, *LR = nullptr, *V32 = nullptr;
+    sc *d_slot = nullptr; // device: delta | wV[0..m) | wc
 };
+static const uint8_t BPG_ZERO32[32] = {0};
 static int verify_prepare(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
-                          size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, vprep &out, sc *d_gh) {
+                          size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, vprep &out, sc *d_gh, sc *d_slot) {
     if (!ctx || !c || !label || !proof || !ext_rng32) return BPG_E_ARG;
     out.status = 0;
     size_t n = c->n, m = c->m;
     if (m && !V32) return BPG_E_ARG;
     // ---- R1CSProof::from_bytes (FormatError -> reject)
     const uint8_t *A[6];
-    uint8_t Z32[32] = {0};
+    const uint8_t *Z32 = BPG_ZERO32;
     const uint8_t *f;
     size_t nf;
     if (flags & BPG_FLAG_LEGACY_FRAMING) {
@@ -521,18 +523,30 @@ static int verify_prepare(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, si
     // vs = [x, a, b, u] at d_small + 3
     k_verify_scalars<<<vb, 128, 0, s>>>((uint32_t)n, (uint32_t)N, d_small + 3, d_w, tyi.lo, tyi.hi, ts.lo, ts.hi, d_g, d_h, d_parts);
     KCHECK();
-    k_sum_partials<1><<<1, 128, 0, s>>>(d_parts, vb, d_small + 48);
+    k_sum_partials<1><<<1, 128, 0, s>>>(d_parts, vb, d_slot);
     KCHECK();
-    sc delta, wc;
-    std::vector<sc> h_wV(m ? m : 1);
-    CUDA_TRY(cudaMemcpyAsync(&delta, d_small + 48, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&wc, d_w + 3 * n + m, 32, cudaMemcpyDeviceToHost, s));
-    if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
-    SYNC_TRY(ctx, s);
-
-    // ---- scalars / points of the single verification MSM
+    CUDA_TRY(cudaMemcpyAsync(d_slot + 1, d_w + 3 * n, 32 * (m + 1), cudaMemcpyDeviceToDevice, s)); // wV[0..m) | wc
+    // the completion half needs these once delta, wV, wc have been read back
+    out.n = n; out.m = m; out.lg = lg; out.x = x; out.u = u; out.r = r; out.w = w; out.tx = tx; out.txb = txb; out.eb = eb;
+    out.ia = ia; out.ibb = ibb;
+    for (size_t j = 0; j < lg; j++) { out.usq[j] = usq[j]; out.uisq[j] = uisq[j]; }
+    for (int i = 0; i < 6; i++) out.A[i] = A[i];
+    out.Tp = Tp; out.LR = LR; out.V32 = V32; out.d_slot = d_slot;
+    out.N = N; out.k = 6 + m + 5 + 2 * lg; out.d_g = d_g; out.d_h = d_h;
+    out.status = 1;
+    return BPG_OK;
+}
+// completion half: scalars / points of the proof's own terms from the read-back slot delta | wV | wc
+static void verify_complete(vprep &out, const sc *h_slot) {
+    const sc &x = out.x, &u = out.u, &r = out.r, &w = out.w;
+    size_t m = out.m, lg = out.lg, k = out.k;
+    const sc &delta = h_slot[0], &wc = h_slot[1 + m];
+    const sc *h_wV = h_slot + 1;
+    const uint8_t *const *A = out.A;
+    const uint8_t *Tp = out.Tp, *LR = out.LR, *V32 = out.V32;
+    const sc &tx = out.tx, &txb = out.txb, &eb = out.eb, &ia = out.ia, &ibb = out.ibb;
+    const sc *usq = out.usq, *uisq = out.uisq;
     sc xx = h_mul(x, x), xxx = h_mul(xx, x), rxx = h_mul(r, xx);
-    size_t k = 6 + m + 5 + 2 * lg;
     std::vector<uint8_t> es(32 * k), ep(32 * k);
     size_t ci = 0;
     auto put = [&](const sc &sv, const uint8_t *pt) { sc_tobytes(es.data() + 32 * ci, sv); memcpy(ep.data() + 32 * ci, pt, 32); ci++; };
@@ -545,9 +559,6 @@ static int verify_prepare(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, si
     sc sBb; sc_neg_r(sBb, h_add(eb, h_mul(r, txb)));
     out.sB = sB; out.sBb = sBb;
     out.es.swap(es); out.ep.swap(ep);
-    out.N = N; out.k = k; out.d_g = d_g; out.d_h = d_h;
-    out.status = 1;
-    return BPG_OK;
 }
 
 // Stage 2: one check  sum_i rho_i * (verification equation of proof i) == identity  over a set of prepared proofs.
@@ -634,8 +645,14 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     *accept = 0;
     if (c && c->m && !V32) return BPG_E_ARG;
     vprep p;
-    CTX_TRY(verify_prepare(ctx, c, label, label_len, V32, proof, proof_len, ext_rng32, flags, p, nullptr));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->scratch[7].ensure((c->m + 4) * sizeof(sc)));
+    CTX_TRY(verify_prepare(ctx, c, label, label_len, V32, proof, proof_len, ext_rng32, flags, p, nullptr, (sc *)ctx->scratch[7].p));
     if (!p.status) return BPG_OK;
+    std::vector<sc> h_slot(c->m + 2);
+    CUDA_TRY(cudaMemcpyAsync(h_slot.data(), p.d_slot, 32 * (c->m + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
+    verify_complete(p, h_slot.data());
     std::vector<vprep *> S = {&p};
     std::vector<sc> rho = {SC_ONE_H};
     return verify_finish(ctx, S, rho, accept);
@@ -683,17 +700,26 @@ extern "C" int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *co
         if (!circuits[i] || !labels[i] || !proofs[i] || (circuits[i]->m && !V32[i])) return BPG_E_ARG;
     }
     // device storage for every proof's g_i | h_i
-    size_t total = 0;
-    std::vector<size_t> goff(count);
-    for (size_t i = 0; i < count; i++) { goff[i] = total; total += 2 * next_pow2(circuits[i]->n) + 8; }
-    CTX_TRY(ctx->batch_gh.ensure(total * sizeof(sc)));
-    sc *d_all = (sc *)ctx->batch_gh.p;
+    size_t total = 0, slots = 0;
+    std::vector<size_t> goff(count), soff(count);
+    for (size_t i = 0; i < count; i++) {
+        goff[i] = total; total += 2 * next_pow2(circuits[i]->n) + 8;
+        soff[i] = slots; slots += circuits[i]->m + 2;
+    }
+    CTX_TRY(ctx->batch_gh.ensure((total + slots + 8) * sizeof(sc)));
+    sc *d_all = (sc *)ctx->batch_gh.p, *d_slots = d_all + total;
     std::vector<vprep> preps(count);
     std::vector<size_t> idx;
+    // every proof's transcript replay (host) and scalar preparation (device) is enqueued back to back; one read-back follows
     for (size_t i = 0; i < count; i++) {
-        CTX_TRY(verify_prepare(ctx, circuits[i], labels[i], label_lens[i], V32[i], proofs[i], proof_lens[i], ext_rng32 + 32 * i, flags, preps[i], d_all + goff[i]));
+        CTX_TRY(verify_prepare(ctx, circuits[i], labels[i], label_lens[i], V32[i], proofs[i], proof_lens[i], ext_rng32 + 32 * i, flags, preps[i], d_all + goff[i],
+                               d_slots + soff[i]));
         if (preps[i].status) idx.push_back(i);
     }
+    std::vector<sc> h_slots(slots + 1);
+    CUDA_TRY(cudaMemcpyAsync(h_slots.data(), d_slots, 32 * slots, cudaMemcpyDeviceToHost, ctx->stream));
+    SYNC_TRY(ctx, ctx->stream);
+    for (size_t i : idx) verify_complete(preps[i], h_slots.data() + soff[i]);
     // weights: rho_i = wide_reduce(SHAKE256("bpg batch" || all ext_rng32 || i))  -- unpredictable to the provers
     std::vector<sc> rhos(count);
     for (size_t i : idx) {

@@ -2,6 +2,7 @@
 // ge25519.cuh) exposed through a C ABI so tests/test_host_arith.py can compare them with the big-int
 // oracle on CPU.  The device bodies (PTX carry chains) are checked on the GPU by tests/test_gpu_*.py.
 #include "../../bulletproofs_gadgets_b200/csrc/consts.h"
+#include "../../bulletproofs_gadgets_b200/csrc/host_scalar64.h"
 bpg_consts h_K;
 extern "C" {
 int ht_init() { return bpg_init_constants_host(); }
@@ -38,6 +39,10 @@ int ht_ilp(const uint8_t *p32, const uint8_t *q32, uint8_t *out) {
     ge_add_ilp(r, p, q); ristretto_encode(out, r);
     ge_dbl_ilp(r, p); ristretto_encode(out + 32, r);
     return 1;
+}
+void ht_sc64(const uint8_t *a, const uint8_t *b, const uint8_t *w64, uint8_t *omul, uint8_t *oinv, uint8_t *owide) {
+    sc x, y; sc_frombytes(x, a); sc_frombytes(y, b);
+    sc_tobytes(omul, bpgh::sc_mul64(x, y)); sc_tobytes(oinv, bpgh::sc_invert64(x)); sc_tobytes(owide, bpgh::sc_wide64(w64));
 }
 void ht_from_uniform(const uint8_t *b64, uint8_t *out) { ge p; ge_from_uniform_bytes(p, b64); ristretto_encode(out, p); }
 }

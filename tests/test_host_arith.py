@@ -87,6 +87,21 @@ def test_scalar_ops(ht):
         assert val(o) == pr.sc_inv(x)
 
 
+def test_host_scalar64_fast_path(ht):
+    """csrc/host_scalar64.h (4 x 64-bit limb products used by the protocol drivers on the host)"""
+    rnd = random.Random(4)
+    edge = [0, 1, Lo - 1, Lo, Lo + 1, 2 ** 252, 2 ** 255 - 1, 2 ** 256 - 1]
+    vals = edge + [rnd.randrange(2 ** 256) for _ in range(300)]
+    om, oi, ow = C.create_string_buffer(32), C.create_string_buffer(32), C.create_string_buffer(32)
+    for x in vals:
+        y = rnd.choice(vals)
+        w = rnd.choice([b"\xff" * 64, bytes(64), rnd.randbytes(64)])
+        ht.ht_sc64(b(x), b(y), w, om, oi, ow)
+        assert val(om) == x * y % Lo
+        assert val(oi) == pow(x % Lo, Lo - 2, Lo)
+        assert val(ow) == int.from_bytes(w, "little") % Lo
+
+
 def test_group_ops_and_ristretto(ht):
     rnd = random.Random(3)
     o = C.create_string_buffer(32)
