@@ -282,10 +282,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
         k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
         KCHECK();
         bool prof = ctx->prof_on && ctx->prof_n < 64; // the first 64 launches after bpg_prof_enable are timed
-        if (prof) {
-            while (ctx->prof_ev.size() < 2 * (ctx->prof_n + 1)) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
-            CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s));
-        }
+        if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s)); // events are pre-created by bpg_prof_enable
         k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
         KCHECK();
         if (prof) {
@@ -487,6 +484,9 @@ extern "C" int bpg_prof_enable(bpg_ctx *ctx, int on) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     SYNC_TRY(ctx, ctx->stream);
     if (on && !ctx->prof_pairs) CUDA_TRY(cudaMallocHost((void **)&ctx->prof_pairs, 4096 * 4));
+    // all events are created here, never in the launch path (event creation takes the context lock and was measured to
+    // slow concurrent provers by a third when done lazily inside the timed region)
+    while (on && ctx->prof_ev.size() < 2 * 64) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
     ctx->prof_on = on;
     if (on) ctx->prof_n = 0;
     return BPG_OK;
