@@ -45,18 +45,6 @@ int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s) {
 }
 #define SYNC_TRY(ctx, s) CTX_TRY(bpg_stream_sync(ctx, s))
 
-static int ensure_pinned(bpg_ctx *ctx, size_t bytes) {
-    if (bytes <= ctx->h_pinned_cap) return BPG_OK;
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
-    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : ctx->tev) if (e) cudaEventDestroy(e);
-    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0;
-    CUDA_TRY(cudaMallocHost(&ctx->h_pinned, bytes + 4096));
-    ctx->h_pinned_cap = bytes + 4096;
-    return BPG_OK;
-}
-
 // ================================================================ context
 extern "C" const char *bpg_strerror(int code) {
     switch (code) {
@@ -160,8 +148,10 @@ extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
     if (!ctx->comb) CUDA_TRY(cudaMalloc((void **)&ctx->comb, (size_t)2 * 32 * 128 * sizeof(ge_an)));
     // SHAKE256 streams on two host threads (sequential squeeze, ~0.3 us per 136 bytes)
     size_t sbytes = 64 * cap;
-    CTX_TRY(ensure_pinned(ctx, 2 * sbytes + 128));
-    uint8_t *hs = (uint8_t *)ctx->h_pinned;
+    // pageable staging: this is a one-off upload, and freeing / re-allocating a large pinned buffer after timing events had
+    // been used made cudaEventDestroy crash on this driver (580.159) -- see tools/repro_teardown.py
+    std::vector<uint8_t> stage(2 * sbytes + 128);
+    uint8_t *hs = stage.data();
     std::thread tg([&] { bpgh::generators_chain_stream('G', 0, hs, cap); });
     bpgh::generators_chain_stream('H', 0, hs + sbytes, cap);
     tg.join();
@@ -484,6 +474,11 @@ extern "C" int bpg_prof_enable(bpg_ctx *ctx, int on) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     SYNC_TRY(ctx, ctx->stream);
     if (on && !ctx->prof_pairs) CUDA_TRY(cudaMallocHost((void **)&ctx->prof_pairs, 4096 * 4));
+    if (!on) { // profiling off: release the events right away (after the sync above)
+        for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+        ctx->prof_ev.clear();
+        ctx->prof_n = 0;
+    }
     // all events are created here, never in the launch path (event creation takes the context lock and was measured to
     // slow concurrent provers by a third when done lazily inside the timed region)
     while (on && ctx->prof_ev.size() < 2 * 64) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
