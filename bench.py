@@ -194,10 +194,11 @@ def run_ours(args):
     per_gpu = cores / max(world, 1)
     if args.provers > 0:
         K = args.provers
-    elif per_gpu >= 12:
-        K = 16                      # enough cores: one spinning host thread per prover (24 sleeping provers measured no better)
     else:
-        K = max(2, min(16, int(1.5 * per_gpu)))  # few cores per GPU (the byte-exact RNG is host-bound): oversubscribe, sleep in syncs
+        # The provers' bulk transcript-RNG draws are batched into SIMD lanes by the library (host_rng_service.h) and the waiting
+        # threads sleep, so the prover count is set by latency hiding (RNG ~45 ms + device ~12 ms per proof at ~200 proofs/s
+        # needs >= 12 proofs in flight), not by the core count.  Measured on 16 cores: K = 16 / 24 / 32 -> 182 / 194 / 191.
+        K = 24
     if K * world > cores:
         os.environ["BPG_BLOCKING_SYNC"] = "1"
     ctx0 = bpg.Context(local)

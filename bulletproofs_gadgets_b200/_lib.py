@@ -45,6 +45,8 @@ SYMBOLS = {
     "bpg_transcript_free": (None, [_vp]),
     "bpg_transcript_append": (None, [_vp, _u8p, _sz, _u8p, _sz]),
     "bpg_transcript_challenge": (None, [_vp, _u8p, _sz, _u8p, _sz]),
+    "bpg_host_rng_lanes": (_i32, []),
+    "bpg_host_rng_draw64": (_i32, [_u8p, _sz, _u8p, _sz, _sz, _i32, _u8p]),
     "bpg_dev_alloc": (_i32, [_vp, _sz, C.POINTER(_vp)]),
     "bpg_dev_free": (_i32, [_vp, _vp]),
     "bpg_dev_upload": (_i32, [_vp, _vp, _u8p, _sz]),

@@ -3,6 +3,7 @@
 #include "bpg_internal.h"
 #include "consts.h"
 #include "host_merlin.h"
+#include "host_rng_service.h"
 #include "host_scalar64.h"
 #include "kernels_core.cuh"
 #include "kernels_msm.cuh"
@@ -543,5 +544,22 @@ extern "C" bpg_transcript *bpg_transcript_new(const uint8_t *label, size_t len) 
 extern "C" void bpg_transcript_free(bpg_transcript *t) { delete t; }
 extern "C" void bpg_transcript_append(bpg_transcript *t, const uint8_t *label, size_t ll, const uint8_t *msg, size_t ml) { t->t.append_raw(label, ll, msg, ml); }
 extern "C" void bpg_transcript_challenge(bpg_transcript *t, const uint8_t *label, size_t ll, uint8_t *out, size_t n) { t->t.challenge_raw(label, ll, out, n); }
+
+// host-only: `count` 64-byte draws of TranscriptRng(Transcript(label)).finalize(ext32) after `warm` scalar draws,
+// through the lane-batched service (use_service = 1) or the scalar definition (0).  Needs no device (CPU tests).
+extern "C" int bpg_host_rng_lanes(void) { return bpgh::RngService::get().lanes(); }
+extern "C" int bpg_host_rng_draw64(const uint8_t *label, size_t label_len, const uint8_t ext32[32], size_t warm, size_t count, int use_service,
+                                   uint8_t *out) {
+    if (!label || !ext32 || (count && !out)) return BPG_E_ARG;
+    bpgh::Transcript t(label, label_len);
+    bpgh::TranscriptRng rng(t);
+    rng.finalize(ext32);
+    uint8_t tmp[64];
+    for (size_t i = 0; i < warm; i++) rng.fill_bytes(tmp, 64);
+    if (use_service) bpgh::RngService::get().draw64(rng, out, count);
+    else for (size_t i = 0; i < count; i++) rng.fill_bytes(out + 64 * i, 64);
+    rng.fill_bytes(out + 64 * count, 64); // one more scalar draw: proves that the stream state was handed back intact
+    return BPG_OK;
+}
 
 #include "prover.inl"

@@ -83,6 +83,18 @@ __global__ void __launch_bounds__(256) k_sc_reduce_inplace(sc *v, uint32_t n) {
     if (i >= n) return;
     sc x; ld_sc(x, &v[i]); sc_reduce(x, x); st_sc(&v[i], x);
 }
+// Scalar::from_bytes_mod_order_wide over raw 64-byte TranscriptRng draws: element i < n goes to outL[i], n <= i < 2n to outR[i - n]
+__global__ void __launch_bounds__(128) k_sc_reduce_wide(const uint32_t *__restrict__ raw, uint32_t n, sc *__restrict__ outL, sc *__restrict__ outR) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const uint4 *src = (const uint4 *)(raw + 16ull * i);
+    u32 R[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint4 q = src[k]; R[4 * k] = q.x; R[4 * k + 1] = q.y; R[4 * k + 2] = q.z; R[4 * k + 3] = q.w; }
+    sc r;
+    sc_reduce512(r, R);
+    st_sc(i < n ? &outL[i] : &outR[i - n], r);
+}
 // lo[t] = base^t (t < 1024), hi[j] = base^(1024 j) (j < nhi)
 __global__ void __launch_bounds__(128) k_pow_tables(const sc *__restrict__ base, sc *__restrict__ lo, sc *__restrict__ hi, uint32_t nhi) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -270,13 +270,17 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         }
         tr.mark("rng(device)");
     } else {
-        std::vector<sc> h_s(2 * n + 1);
-        for (size_t i = 0; i < 2 * n; i++) h_s[i] = rng_scalar(rng);
+        // The raw 64-byte draws come from the lane-batched RNG service (one Keccak-f per draw, shared SIMD registers with the
+        // other provers of this process); Scalar::from_bytes_mod_order_wide happens on the device.
+        std::vector<uint8_t> raw(128 * n + 64);
+        bpgh::RngService::get().draw64(rng, raw.data(), 2 * n);
         tr.mark("rng");
         if (n) {
-            CUDA_TRY(cudaMemcpyAsync(d_sL, h_s.data(), 32 * n, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(d_sR, h_s.data() + n, 32 * n, cudaMemcpyHostToDevice, s));
-            SYNC_TRY(ctx, s); // h_s is released at the end of this scope
+            CTX_TRY(ctx->scratch[12].ensure((4 * N + 8) * sizeof(sc))); // l1|r0|r1|r3 later; free until the commit MSMs are done
+            CUDA_TRY(cudaMemcpyAsync(ctx->scratch[12].p, raw.data(), 128 * n, cudaMemcpyHostToDevice, s));
+            k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)ctx->scratch[12].p, (uint32_t)n, d_sL, d_sR);
+            KCHECK();
+            SYNC_TRY(ctx, s); // raw is released at the end of this scope
         }
     }
     memset(&plan, 0, sizeof plan);

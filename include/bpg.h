@@ -126,6 +126,14 @@ bpg_transcript *bpg_transcript_new(const uint8_t *label, size_t len);
 void bpg_transcript_free(bpg_transcript *t);
 void bpg_transcript_append(bpg_transcript *t, const uint8_t *label, size_t ll, const uint8_t *msg, size_t ml);
 void bpg_transcript_challenge(bpg_transcript *t, const uint8_t *label, size_t ll, uint8_t *out, size_t n);
+/* merlin TranscriptRng (the prover's source of blinding factors; Prover::prove behind src/bin/prover.rs:93).  Concurrent
+ * provers of one process share a lane-batched Keccak (4 streams per AVX2 / 8 per AVX-512 register file);
+ * bpg_host_rng_lanes() reports the width in use (1 = scalar; BPG_RNG_LANES=1 forces it).  bpg_host_rng_draw64 writes
+ * count + 1 draws of 64 bytes of TranscriptRng(Transcript(label)).finalize(ext32) after `warm` discarded draws: the
+ * first `count` through the service (use_service = 1) or the scalar definition (0), the last one always scalar. */
+int bpg_host_rng_lanes(void);
+int bpg_host_rng_draw64(const uint8_t *label, size_t label_len, const uint8_t ext32[32], size_t warm, size_t count, int use_service,
+                        uint8_t *out);
 
 /* device memory helpers for callers that keep vectors resident (bench, multi-GPU drivers) */
 int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr);
