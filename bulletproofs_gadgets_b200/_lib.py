@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libbpg.so")
 
 OK, E_CUDA, E_SIZE, E_DECOMPRESS, E_ARG, E_FORMAT, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 FLAG_LEGACY_FRAMING, FLAG_FAST_BLINDING, FLAG_WITNESS_ON_DEVICE = 1, 2, 4
+FLAG_NO_LATE_FOLD, FLAG_FORCE_LATE_FOLD = 8, 16
 
 # every symbol include/bpg.h declares: name -> (restype, argtypes)
 _u8p, _sz, _i32, _vp = C.c_char_p, C.c_size_t, C.c_int, C.c_void_p
@@ -55,6 +56,7 @@ SYMBOLS = {
     "bpg_event_elapsed_ms": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_float)]),
     "bpg_prof_enable": (_i32, [_vp, _i32]),
     "bpg_prof_read": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "bpg_prof_read_launches": (C.c_long, [_vp, C.POINTER(C.c_float), _u32p, _sz]),
     "bpg_bench_latency": (_i32, [_vp, _i32, C.POINTER(C.c_double)]),
     "bpg_bench_imad": (_i32, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
 }

@@ -185,6 +185,14 @@ class Context:
         self.check(self.lib.bpg_prof_read(self.h, C.byref(n), C.byref(ms), C.byref(pairs)))
         return n.value, ms.value, pairs.value
 
+    def prof_read_launches(self, cap=64):
+        """[(ms, pairs)] of every timed k_msm_accumulate launch since prof_enable(True)"""
+        ms, pairs = (C.c_float * cap)(), (C.c_uint32 * cap)()
+        n = self.lib.bpg_prof_read_launches(self.h, ms, pairs, cap)
+        if n < 0:
+            self.check(n)
+        return [(ms[i], pairs[i]) for i in range(n)]
+
     def sync(self):
         self.check(self.lib.bpg_sync(self.h))
 

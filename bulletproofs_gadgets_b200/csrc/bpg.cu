@@ -95,6 +95,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
     ctx->batch_gh.release();
+    ctx->mat_pts.release(); ctx->mat_ext.release(); ctx->mat_tab.release();
     DSTEP("buffers freed");
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
@@ -233,13 +234,11 @@ static int run_points_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, size_t n, ge 
     return BPG_OK;
 }
 
-int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
-    uint32_t total = 0;
-    for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
-    plan->total = total;
-    int G = plan->ngroups;
-    uint32_t nb = (uint32_t)G * BPG_NBP;
-    size_t maxpairs = (size_t)total * BPG_NWIN;
+// Common front half of every bucket MSM: histogram -> scan -> counting-sort scatter -> chunked accumulation -> per-bucket
+// finish.  `digits(scatter, counters_or_cursor, sorted)` launches the recoding kernel of the caller (k_msm_digits for plain
+// MSMs, k_mat_digits for the multi-output fold).  Leaves the nb bucket sums in ctx->buckets.
+template <class DigitsLaunch>
+static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpairs, bool any, const ge_an *tab, DigitsLaunch &&digits) {
     // chunk = sorted pairs summed by one thread: sized so that the accumulate grid has >= ~8 warps per SM sub-partition
     // (two full waves of 4 blocks x 128 threads on 148 SMs = 151 552 threads)
     uint32_t CH = (uint32_t)((maxpairs + 151551) / 151552);
@@ -247,34 +246,29 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     if (CH > BPG_CHUNK) CH = BPG_CHUNK;
     size_t nchunks = (maxpairs + CH - 1) / CH + 1;
     uint32_t ntiles = (nb + 1023) / 1024;
-    CTX_TRY(ctx->counts.ensure((nb + 2 + ntiles + 2) * 4)); // counters, then the scan's ticket + per-tile totals
-    CTX_TRY(ctx->offsets.ensure((nb + 2) * 4));
-    CTX_TRY(ctx->cursor.ensure((nb + 2) * 4));
+    CTX_TRY(ctx->counts.ensure(((size_t)nb + 2 + ntiles + 2) * 4)); // counters, then the scan's ticket + per-tile totals
+    CTX_TRY(ctx->offsets.ensure(((size_t)nb + 2) * 4));
+    CTX_TRY(ctx->cursor.ensure(((size_t)nb + 2) * 4));
     CTX_TRY(ctx->sorted.ensure((maxpairs + 1) * 4));
     CTX_TRY(ctx->partial.ensure(2 * nchunks * sizeof(ge)));
     CTX_TRY(ctx->buckets.ensure((size_t)nb * sizeof(ge)));
-    CTX_TRY(ctx->heavy.ensure((nb + 2) * 4));
-    CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
-    CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
+    CTX_TRY(ctx->heavy.ensure(((size_t)nb + 2) * 4));
     uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *heavy = (uint32_t *)ctx->heavy.p;
-    CUDA_TRY(cudaMemsetAsync(counts, 0, (nb + 2 + ntiles + 2) * 4, s));
+    CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)nb + 2 + ntiles + 2) * 4, s));
     CUDA_TRY(cudaMemsetAsync(heavy + nb + 1, 0, 4, s));
-    msm_params P;
-    memcpy(P.seg, plan->seg, sizeof(P.seg));
-    P.nseg = plan->nseg; P.total = total; P.ptotal = ctx->ptotal;
-    if (total) {
-        k_msm_digits<0><<<LAUNCH_1D(total, 256), 0, s>>>(P, counts, nullptr);
+    if (any) {
+        digits(0, counts, (uint32_t *)nullptr);
         KCHECK();
     }
     k_msm_scan<<<ntiles, 256, 0, s>>>(counts, nb, offsets, cursor, counts + nb + 2);
     KCHECK();
-    if (total) {
-        k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cursor, (uint32_t *)ctx->sorted.p);
+    if (any) {
+        digits(1, cursor, (uint32_t *)ctx->sorted.p);
         KCHECK();
         bool prof = ctx->prof_on && ctx->prof_n < 64; // the first 64 launches after bpg_prof_enable are timed
         if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s)); // events are pre-created by bpg_prof_enable
-        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, ctx->tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
+        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
         KCHECK();
         if (prof) {
             CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], s));
@@ -284,10 +278,29 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     }
     k_msm_finish<<<LAUNCH_1D(nb, 64), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
     KCHECK();
-    if (total) {
+    if (any) {
         k_msm_heavy<<<64, 64, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
         KCHECK();
     }
+    return BPG_OK;
+}
+
+int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
+    uint32_t total = 0;
+    for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
+    plan->total = total;
+    int G = plan->ngroups;
+    uint32_t nb = (uint32_t)G * BPG_NBP;
+    CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
+    CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
+    msm_params P;
+    memcpy(P.seg, plan->seg, sizeof(P.seg));
+    P.nseg = plan->nseg; P.total = total; P.ptotal = plan->tab ? plan->ptotal : ctx->ptotal;
+    const ge_an *tab = plan->tab ? plan->tab : ctx->tab;
+    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN, total != 0, tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+        if (scatter) k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+        else k_msm_digits<0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+    }));
     // weighted sum over the 129 x 256 bucket matrix: row/column sums, small-weight multiples, combine
     ge *rc = (ge *)ctx->lvlP.p, *out2 = (ge *)ctx->lvlQ.p;
     k_msm_rowcol<<<dim3(BPG_NROWS + BPG_NCOLS, G), 64, 0, s>>>((const ge *)ctx->buckets.p, rc);
@@ -295,6 +308,30 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     k_msm_wfinal<<<dim3(8, G), 64, 0, s>>>(rc, out2);
     KCHECK();
     k_msm_combine<<<G, 32, 0, s>>>(out2, d_out);
+    KCHECK();
+    return BPG_OK;
+}
+
+// Late fold (see kernels_msm.cuh): G^(k)_i, H^(k)_i for i < n' from the per-generator factors EG, EH (length N), then the
+// 16-window affine-Niels tables of those 2 n' points (+ B) in ctx->mat_tab with 2 n' + 2 points per window.
+int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH) {
+    uint32_t nout = 2 * nprime;
+    uint32_t nb = 2 * nout * BPG_MAT_NB;
+    uint32_t pt_small = nout + 2;
+    CTX_TRY(ctx->mat_pts.ensure((size_t)nout * sizeof(ge)));
+    CTX_TRY(ctx->mat_ext.ensure((size_t)BPG_NWIN * nout * sizeof(ge)));
+    CTX_TRY(ctx->mat_tab.ensure((size_t)BPG_NWIN * pt_small * sizeof(ge_an)));
+    uint32_t cap = (uint32_t)ctx->cap, ptotal = ctx->ptotal;
+    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)2 * N * BPG_NWIN * 2, true, ctx->tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+        if (scatter) k_mat_digits<1><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
+        else k_mat_digits<0><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
+    }));
+    k_mat_reduce<<<nout, 32, 0, s>>>((const ge *)ctx->buckets.p, nout, (ge *)ctx->mat_pts.p);
+    KCHECK();
+    k_mat_chain<<<LAUNCH_1D(nout, 64), 0, s>>>((const ge *)ctx->mat_pts.p, nout, (ge *)ctx->mat_ext.p);
+    KCHECK();
+    k_mat_affine<<<LAUNCH_1D(BPG_NWIN * nout + BPG_NWIN, 64), 0, s>>>((const ge *)ctx->mat_ext.p, nout, pt_small, (ge_an *)ctx->mat_tab.p, ctx->tab, ptotal,
+                                                                      2 * cap);
     KCHECK();
     return BPG_OK;
 }
@@ -498,6 +535,17 @@ extern "C" int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total,
     }
     *launches = ctx->prof_n; *ms_total = ms; *pairs_total = pairs;
     return BPG_OK;
+}
+
+extern "C" long bpg_prof_read_launches(bpg_ctx *ctx, float *ms, uint32_t *pairs, size_t cap) {
+    if (!ctx || !ms || !pairs) return BPG_E_ARG;
+    SYNC_TRY(ctx, ctx->stream);
+    size_t n = ctx->prof_n < cap ? ctx->prof_n : cap;
+    for (size_t i = 0; i < n; i++) {
+        CUDA_TRY(cudaEventElapsedTime(&ms[i], ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        pairs[i] = ctx->prof_pairs[i];
+    }
+    return (long)n;
 }
 
 extern "C" int bpg_bench_imad(bpg_ctx *ctx, int iters, float *ms, double *mac32) {

@@ -30,7 +30,11 @@ struct msm_seg {
     uint32_t start;    // filled by msm_run: global term index of term 0
     uint32_t alt;      // 0, or 1 + k: group ^= bit k of the term's index inside the segment (IPP rounds: left/right halves)
 };
-struct msm_plan { msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total; };
+struct msm_plan {
+    msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total;
+    const ge_an *tab;   // window tables the point indices refer to (nullptr: the resident generators, ctx->tab)
+    uint32_t ptotal;    // points per window of `tab`
+};
 
 struct dev_buf { // grow-only device buffer
     void *p = nullptr; size_t cap = 0;
@@ -52,6 +56,7 @@ struct bpg_ctx {
     // generic scratch
     dev_buf scratch[16];
     dev_buf batch_gh;         // batch verification: every proof's g | h scalars
+    dev_buf mat_pts, mat_ext, mat_tab; // late fold: materialised G^(k) | H^(k), their window chain, their affine-Niels tables
     void *h_pinned = nullptr; size_t h_pinned_cap = 0;
     cudaEvent_t tev[16] = {nullptr};
     int prof_on = 0;
@@ -65,3 +70,5 @@ struct bpg_ctx {
 // bpg.cu
 int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s);
 int msm_run(bpg_ctx *c, cudaStream_t s, msm_plan *plan, ge *d_out /* ngroups extended points */);
+// late fold (kernels_msm.cuh): tables of the 2 n' folded generators (+ B at index 2 n') into ctx->mat_tab, ptotal = 2 n' + 2
+int msm_materialise_fold(bpg_ctx *c, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH);

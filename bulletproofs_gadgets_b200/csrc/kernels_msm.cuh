@@ -318,3 +318,143 @@ __global__ void __launch_bounds__(32) k_msm_combine(const ge *__restrict__ in8, 
     }
     if (t == 0) st_ge(&out[g], acc);
 }
+
+// =====================================================================================================================
+// Late fold: materialise the folded generators G^(k), H^(k) of the inner-product argument once, after k rounds.
+//
+// dalek's InnerProductProof::create (behind src/bin/prover.rs:93) folds the generator vectors in every round.  Here the
+// first k rounds are evaluated over the original generators with expanded scalars (k_ipp_expand); every later round would
+// still pay a full 2N-term MSM although only n' = N / 2^k folded generators remain.  So at round k the folded generators
+//     G^(k)_i = sum_{p = i (mod n')} EG[p] G_p ,   H^(k)_i = sum_{p = i (mod n')} EH[p] H_p        (i < n')
+// are computed as ONE multi-output MSM over the resident window tables (2 n' outputs), 16-window tables are built for
+// them, and the remaining rounds run the same engine over those 2 n' points -- a few thousand pairs instead of 2N * 16.
+//
+// Multi-output MSM: an output has only N / n' * 16 pairs, too few for 2^15 buckets.  Each signed 16-bit digit d of a
+// (term, window) pair is split again, d = dl + 256 dh with dl in [-128, 127], dh in [-128, 128], and the SAME table entry
+// 2^(16w) P goes to bucket |dl| of the output's "low" set and to bucket |dh| of its "high" set (2 x 129 buckets per
+// output, no extra tables, no doublings).  Output = sum_b b * low_b + 256 * sum_b b * high_b.
+// The sort / accumulate / finish kernels above are reused unchanged (bucket = (2 * output + set) * 129 + |digit|).
+#define BPG_MAT_NB 129u
+template <int SCATTER>
+__global__ void __launch_bounds__(256) k_mat_digits(uint32_t N, uint32_t nprime, uint32_t cap, uint32_t ptotal, const sc *__restrict__ EG, const sc *__restrict__ EH,
+                                                     uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * N) return;
+    bool isH = t >= N;
+    uint32_t p = isH ? t - N : t;
+    sc k;
+    ld_sc(k, isH ? &EH[p] : &EG[p]);
+    int d[16];
+    sc_digits16(d, k);
+    uint32_t out = (p & (nprime - 1)) + (isH ? nprime : 0u);
+    uint32_t pidx = p + (isH ? cap : 0u);
+    uint32_t base = 2u * out * BPG_MAT_NB;
+#pragma unroll
+    for (int w = 0; w < 16; w++) {
+        int dw = d[w];
+        if (dw == 0) continue;
+        int dl = ((dw + 128) & 255) - 128;   // [-128, 127]
+        int dh = (dw - dl) >> 8;             // exact: dw - dl is a multiple of 256 ; [-128, 128]
+        uint32_t ent = (uint32_t)w * ptotal + pidx;
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+            int dd = part ? dh : dl;
+            if (dd == 0) continue;
+            uint32_t mag = dd < 0 ? (uint32_t)(-dd) : (uint32_t)dd;
+            uint32_t bkt = base + part * BPG_MAT_NB + mag;
+            if (SCATTER) {
+                uint32_t pos = atomicAdd(&counts_or_cursor[bkt], 1u);
+                sorted[pos] = ent | (dd < 0 ? 0x80000000u : 0u);
+            } else {
+                atomicAdd(&counts_or_cursor[bkt], 1u);
+            }
+        }
+    }
+}
+// One 32-thread block per output.  Lane = (set, segment): set = lane >> 3 (0 low, 1 high), segment s = lane & 7 covers
+// buckets 16 s + 1 .. 16 s + 16.  Running sums give seg_sum = sum T_b and seg_w = sum (b - 16 s) T_b; the lane's value is
+// seg_w + 16 s * seg_sum; lanes of a set are tree-summed, and the output is low + 2^8 high.
+__global__ void __launch_bounds__(32) k_mat_reduce(const ge *__restrict__ buckets, uint32_t nout, ge *__restrict__ out) {
+    __shared__ ge smem[16];
+    uint32_t o = blockIdx.x, lane = threadIdx.x;
+    if (o >= nout) return;
+    if (lane < 16) {
+        uint32_t set = lane >> 3, seg = lane & 7;
+        const ge *B = buckets + ((size_t)2 * o + set) * BPG_MAT_NB + 16u * seg;
+        ge run, acc, q;
+        ge_identity(run); ge_identity(acc);
+#pragma unroll 1
+        for (int b = 16; b >= 1; b--) {
+            ld_ge(q, &B[b]);
+            ge_add_ilp(run, run, q);
+            ge_add_ilp(acc, acc, run);
+        }
+        // acc += 16 * seg * run
+        ge m;
+        ge_small_mul(m, seg, run);
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) ge_dbl_ilp(m, m);
+        ge_add_ilp(acc, acc, m);
+        st_ge(&smem[lane], acc);
+    }
+    __syncwarp();
+    for (int s2 = 4; s2 > 0; s2 >>= 1) {
+        if (lane < 16 && (lane & 7) < (uint32_t)s2) {
+            ge a, b;
+            ld_ge(a, &smem[lane]); ld_ge(b, &smem[lane + s2]);
+            ge_add_ilp(a, a, b);
+            st_ge(&smem[lane], a);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        ge lo, hi;
+        ld_ge(lo, &smem[0]); ld_ge(hi, &smem[8]);
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) ge_dbl_ilp(hi, hi);
+        ge_add_ilp(lo, lo, hi);
+        st_ge(&out[o], lo);
+    }
+}
+// window chain of the materialised points: ext[w][q] = 2^(16 w) P_q  (one thread per point, 240 doublings)
+__global__ void __launch_bounds__(64) k_mat_chain(const ge *__restrict__ pts, uint32_t npts, ge *__restrict__ ext) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    ge p;
+    ld_ge(p, &pts[q]);
+#pragma unroll 1
+    for (int w = 0; w < BPG_NWIN; w++) {
+        st_ge(&ext[(size_t)w * npts + q], p);
+        if (w + 1 < BPG_NWIN) {
+#pragma unroll 1
+            for (int k = 0; k < BPG_WBITS; k++) ge_dbl_ilp(p, p);
+        }
+    }
+}
+// affine-Niels table of the materialised points (one thread per (window, point): its own inversion), plus the entries of
+// one resident point (B) copied from the main table to index npts
+__global__ void __launch_bounds__(64) k_mat_affine(const ge *__restrict__ ext, uint32_t npts, uint32_t ptotal_small, ge_an *__restrict__ tab_small,
+                                                    const ge_an *__restrict__ tab_main, uint32_t ptotal_main, uint32_t pB_main) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = BPG_NWIN * npts;
+    if (t < total) {
+        uint32_t w = t / npts, q = t - w * npts;
+        ge p;
+        ld_ge(p, &ext[t]);
+        ge_an a;
+        ge_to_an(a, p);
+        st_an(&tab_small[(size_t)w * ptotal_small + q], a);
+    } else if (t < total + BPG_NWIN) {
+        uint32_t w = t - total;
+        ge_an a;
+        ld_an(a, &tab_main[(size_t)w * ptotal_main + pB_main]);
+        st_an(&tab_small[(size_t)w * ptotal_small + npts], a);
+    }
+}
+__global__ void __launch_bounds__(128) k_sc_fill_one(sc *__restrict__ v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc one;
+    sc_set_u32(one, 1);
+    st_sc(&v[i], one);
+}

@@ -366,8 +366,27 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     t.append_u64("n", N);
     sc *d_sG = (sc *)ctx->scratch[12].p, *d_sH = d_sG + N; // l1.. are dead now
     std::vector<uint8_t> LR(64 * (lgN ? lgN : 1));
+    // Late fold (kernels_msm.cuh): rounds j < k0 run over the N original generators with expanded scalars; at round k0 the
+    // n' = N >> k0 folded generators are materialised and the remaining rounds run over them (EG = EH = 1 again).
+    int k0 = lgN; // no late fold
+    bool late = (flags & BPG_FLAG_FORCE_LATE_FOLD) ? lgN >= 2 : (!(flags & BPG_FLAG_NO_LATE_FOLD) && lgN >= 15);
+    if (late) k0 = std::max(1, lgN - 9);
+    size_t Ncur = N;                       // generators of the current basis
+    uint32_t pG = 0, pH = (uint32_t)ctx->cap, pQ = pB; // point indices of G_0, H_0 and B in the current tables
+    const ge_an *tabcur = nullptr;
+    uint32_t ptcur = 0;
     for (int j = 0; j < lgN; j++) {
         uint32_t nj = (uint32_t)(N >> j), h = nj >> 1;
+        if (j == k0) {
+            CTX_TRY(msm_materialise_fold(ctx, s, (uint32_t)N, nj, d_EG, d_EH));
+            Ncur = nj;
+            tabcur = (const ge_an *)ctx->mat_tab.p; ptcur = 2 * nj + 2;
+            pG = 0; pH = nj; pQ = 2 * nj;
+            k_sc_fill_one<<<LAUNCH_1D(Ncur, 128), 0, s>>>(d_EG, (uint32_t)Ncur);
+            KCHECK();
+            k_sc_fill_one<<<LAUNCH_1D(Ncur, 128), 0, s>>>(d_EH, (uint32_t)Ncur);
+            KCHECK();
+        }
         unsigned cb = (unsigned)std::min<size_t>((h + 127) / 128, 1184);
         k_ipp_cross<<<cb, 128, 0, s>>>(h, d_a, d_b, d_parts);
         KCHECK();
@@ -375,14 +394,15 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_ipp_cw<<<1, 32, 0, s>>>(d_small + 24, d_small + 10, d_small + 13);
         KCHECK();
-        k_ipp_expand<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)N, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
+        k_ipp_expand<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
         KCHECK();
         memset(&plan, 0, sizeof plan);
         plan.ngroups = 2;
-        add_seg(d_sG, N, 0, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h);                 // G_i: right half -> L (group 0)
-        add_seg(d_sH, N, (uint32_t)ctx->cap, 0); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // H_i: right half -> R (group 1)
-        add_seg(d_small + 13, 1, pB, 0);
-        add_seg(d_small + 14, 1, pB, 1);
+        plan.tab = tabcur; plan.ptotal = ptcur;
+        add_seg(d_sG, Ncur, pG, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // G_i: right half -> L (group 0)
+        add_seg(d_sH, Ncur, pH, 0); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // H_i: right half -> R (group 1)
+        add_seg(d_small + 13, 1, pQ, 0);
+        add_seg(d_small + 14, 1, pQ, 1);
         CTX_TRY(msm_run(ctx, s, &plan, res));
         CTX_TRY(run_compress(ctx, s, res, 2, d_enc));
         CUDA_TRY(cudaMemcpyAsync(LR.data() + 64 * j, d_enc, 64, cudaMemcpyDeviceToHost, s));
@@ -392,7 +412,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         sc uj = challenge_scalar(t, "u");
         sc uu[2] = {uj, h_inv(uj)};
         CUDA_TRY(cudaMemcpyAsync(d_small + 11, uu, sizeof uu, cudaMemcpyHostToDevice, s));
-        k_ipp_fold<<<LAUNCH_1D(N, 128), 0, s>>>((uint32_t)N, nj, d_small + 11, d_a, d_b, d_EG, d_EH);
+        k_ipp_fold<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_small + 11, d_a, d_b, d_EG, d_EH);
         KCHECK();
     }
     tr.mark("ipp");

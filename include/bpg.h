@@ -40,6 +40,11 @@ typedef struct bpg_circuit bpg_circuit;
 #define BPG_FLAG_WITNESS_ON_DEVICE 4u /* aL, aR, aO are device pointers to reduced scalars (HBM-resident timing) */
 #define BPG_FLAG_FAST_BLINDING 2u  /* s_L, s_R expanded on the device from a transcript-derived seed instead of
                                       2n sequential Merlin TranscriptRng draws: valid proofs, different bytes */
+/* Inner-product argument: after the first rounds the folded generators G^(k), H^(k) (512 each) are materialised once by a
+ * multi-output MSM and the remaining rounds run over them (same L_j, R_j bytes, ~1/3 fewer point additions per proof).
+ * On by default for padded sizes >= 2^15; these two flags force it off / on (any size >= 4) for tests and A/B timing. */
+#define BPG_FLAG_NO_LATE_FOLD 8u
+#define BPG_FLAG_FORCE_LATE_FOLD 16u
 
 int bpg_ctx_create(int device, bpg_ctx **out);
 void bpg_ctx_destroy(bpg_ctx *ctx);
@@ -149,6 +154,8 @@ int bpg_event_elapsed_ms(bpg_ctx *ctx, int slot_a, int slot_b, float *ms);
  * number of (term, window) pairs they accumulated since the last enable */
 int bpg_prof_enable(bpg_ctx *ctx, int on);
 int bpg_prof_read(bpg_ctx *ctx, uint64_t *launches, double *ms_total, uint64_t *pairs_total);
+/* the same, launch by launch (up to cap): duration in ms and sorted pairs of each timed k_msm_accumulate launch; returns the count */
+long bpg_prof_read_launches(bpg_ctx *ctx, float *ms, uint32_t *pairs, size_t cap);
 
 /* integer-pipe microbenchmark: runs `iters` dependent field multiplications per thread over a full-chip grid and
  * returns elapsed milliseconds (CUDA events) and the number of 32x32->64 multiply-accumulates executed */

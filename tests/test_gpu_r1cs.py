@@ -162,3 +162,19 @@ def test_reference_style_api_roundtrip(ctx):
         else:
             with pytest.raises(bpg.R1CSError):
                 verifier.verify(proof, None, bp)
+
+
+@pytest.mark.parametrize("nmul,seed", [(3, 21), (4, 22), (5, 23), (8, 24), (13, 25), (64, 26), (100, 27), (300, 28), (700, 29), (1500, 30)])
+def test_late_fold_proof_bytes_match_oracle(ctx, nmul, seed):
+    """Late fold (materialised G^(k), H^(k) after the first IPP rounds, kernels_msm.cuh): same L_j / R_j, hence the same proof
+    bytes as the oracle (which folds the generators in every round like dalek) and as the path without it."""
+    import bulletproofs_gadgets_b200._lib as lb
+    inst = circuits.chain_instance(nmul, seed)
+    ext = bytes(range(1, 33))
+    want, Vw = oracle_prove(inst, 2048, ext)
+    forced, V1 = gpu_prove(ctx, inst, ext, lb.FLAG_FORCE_LATE_FOLD)
+    plain, V2 = gpu_prove(ctx, inst, ext, lb.FLAG_NO_LATE_FOLD)
+    assert V1 == V2 == Vw
+    assert forced == want
+    assert plain == want
+    assert gpu_verify(ctx, inst, V1, forced)
