@@ -290,16 +290,29 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
     plan->total = total;
     int G = plan->ngroups;
-    uint32_t nb = (uint32_t)G * BPG_NBP;
-    CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
-    CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
     msm_params P;
     memcpy(P.seg, plan->seg, sizeof(P.seg));
     P.nseg = plan->nseg; P.total = total; P.ptotal = plan->tab ? plan->ptotal : ctx->ptotal;
     const ge_an *tab = plan->tab ? plan->tab : ctx->tab;
+    if (total <= BPG_SMALL_MSM_TERMS) {
+        // Small MSM (late IPP rounds over the materialised generators, small circuits): the 2 x 2^15-bucket reduction below
+        // would cost more than the accumulation.  Split every 16-bit digit into two 8-bit digits instead (two pairs per
+        // digit, 2 x 129 buckets per group) and reduce each group with one k_mat_reduce block.
+        uint32_t nb = (uint32_t)G * 2u * BPG_MAT_NB;
+        CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN * 2, total != 0, tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+            if (scatter) k_msm_digits<1, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+            else k_msm_digits<0, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+        }));
+        k_mat_reduce<<<G, 32, 0, s>>>((const ge *)ctx->buckets.p, (uint32_t)G, d_out);
+        KCHECK();
+        return BPG_OK;
+    }
+    uint32_t nb = (uint32_t)G * BPG_NBP;
+    CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
+    CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
     CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN, total != 0, tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
-        if (scatter) k_msm_digits<1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
-        else k_msm_digits<0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+        if (scatter) k_msm_digits<1, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
+        else k_msm_digits<0, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
     }));
     // weighted sum over the 129 x 256 bucket matrix: row/column sums, small-weight multiples, combine
     ge *rc = (ge *)ctx->lvlP.p, *out2 = (ge *)ctx->lvlQ.p;

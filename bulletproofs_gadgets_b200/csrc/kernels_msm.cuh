@@ -40,7 +40,10 @@ __device__ __forceinline__ void sc_digits16(int *d, const sc &k) {
     }
 }
 
-template <int SCATTER>
+// SPLIT = 0: bucket = group * BPG_NBP + |d|                               (2^15 buckets per group, one pair per digit)
+// SPLIT = 1: d = dl + 256 dh, buckets (2 group + 0) * 129 + |dl| and (2 group + 1) * 129 + |dh|   (small MSMs: 2 x 129 buckets
+//            per group and two pairs per digit, reduced by k_mat_reduce -- see the late-fold section below)
+template <int SCATTER, int SPLIT>
 __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.total) return;
@@ -57,18 +60,37 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     sc_digits16(d, k);
     uint32_t grp = S.group;
     if (S.alt) grp ^= (j >> (S.alt - 1)) & 1u;
-    uint32_t base = grp * BPG_NBP;
+    uint32_t base = SPLIT ? grp * 2u * 129u : grp * BPG_NBP;
     uint32_t pidx = S.p0 + j;
 #pragma unroll
     for (int w = 0; w < 16; w++) {
         int dw = d[w];
         if (dw == 0) continue;
-        uint32_t mag = dw < 0 ? (uint32_t)(-dw) : (uint32_t)dw;
-        if (SCATTER) {
-            uint32_t pos = atomicAdd(&counts_or_cursor[base + mag], 1u);
-            sorted[pos] = ((uint32_t)w * P.ptotal + pidx) | (dw < 0 ? 0x80000000u : 0u);
+        uint32_t ent = (uint32_t)w * P.ptotal + pidx;
+        if (SPLIT) {
+            int dl = ((dw + 128) & 255) - 128; // [-128, 127]
+            int dh = (dw - dl) >> 8;           // exact ; [-128, 128]
+#pragma unroll
+            for (int part = 0; part < 2; part++) {
+                int dd = part ? dh : dl;
+                if (dd == 0) continue;
+                uint32_t mag = dd < 0 ? (uint32_t)(-dd) : (uint32_t)dd;
+                uint32_t bkt = base + part * 129u + mag;
+                if (SCATTER) {
+                    uint32_t pos = atomicAdd(&counts_or_cursor[bkt], 1u);
+                    sorted[pos] = ent | (dd < 0 ? 0x80000000u : 0u);
+                } else {
+                    atomicAdd(&counts_or_cursor[bkt], 1u);
+                }
+            }
         } else {
-            atomicAdd(&counts_or_cursor[base + mag], 1u);
+            uint32_t mag = dw < 0 ? (uint32_t)(-dw) : (uint32_t)dw;
+            if (SCATTER) {
+                uint32_t pos = atomicAdd(&counts_or_cursor[base + mag], 1u);
+                sorted[pos] = ent | (dw < 0 ? 0x80000000u : 0u);
+            } else {
+                atomicAdd(&counts_or_cursor[base + mag], 1u);
+            }
         }
     }
 }
