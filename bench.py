@@ -161,6 +161,41 @@ def msm_sweep(ctx, sizes, reps=5):
     return out
 
 
+def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5):
+    """ONE MSM of n points split by point range over the ranks (parallel.msm_gens_sharded): every rank
+    sums its slice of the resident generators, the 128-byte partial points are all-gathered over NCCL and added on every rank.
+    Timed on the host around barrier + synchronize (the collective runs on torch's stream), max over ranks."""
+    import ctypes as C
+    import numpy as np
+    from bulletproofs_gadgets_b200 import parallel
+    out = {}
+    maxn = max(sizes)
+    ctx.gens_ensure(maxn // 2)
+    rng = np.random.default_rng(7)
+    dev = "cuda:%d" % local
+    for n in sizes:
+        h = n // 2
+        lo, hi = parallel.shard_range(h, rank, world)
+        raw = rng.integers(0, 256, size=(2 * h, 32), dtype=np.uint8)  # same stream on every rank: sG | sH
+        raw[:, 31] &= 0x0F
+        mine = np.concatenate([raw[lo:hi], raw[h + lo:h + hi]])
+        d = ctx.dev_alloc(32 * len(mine))
+        ctx.dev_upload(d, mine.tobytes())
+        dG, dH = d, C.c_void_p(d.value + 32 * (hi - lo))
+        first = parallel.msm_gens_sharded(ctx, dG, dH, h, dev)  # warm-up, and a cross-rank agreement check
+        agree = parallel.allgather_bytes(first, dev)
+        if any(a != first for a in agree):
+            raise SystemExit("sharded MSM: ranks disagree on the result")
+        barrier_max(dist, local, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            parallel.msm_gens_sharded(ctx, dG, dH, h, dev)
+        ms = barrier_max(dist, local, (time.perf_counter() - t0) * 1e3 / reps)
+        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3, "points_per_rank": 2 * (hi - lo)}
+        ctx.dev_free(d)
+    return out
+
+
 class ProverLane:
     """one host thread's private context: own bpg_ctx (stream, workspace, tables), circuit copy and HBM-resident witness"""
 
@@ -196,9 +231,10 @@ def run_ours(args):
         K = args.provers
     else:
         # The provers' bulk transcript-RNG draws are batched into SIMD lanes by the library (host_rng_service.h) and the waiting
-        # threads sleep, so the prover count is set by latency hiding (RNG ~45 ms + device ~12 ms per proof at ~200 proofs/s
-        # needs >= 12 proofs in flight), not by the core count.  Measured on 16 cores: K = 16 / 24 / 32 -> 182 / 194 / 191.
-        K = 24
+        # threads sleep, so the prover count is set by latency hiding, not by the core count: a proof spends ~60-100 ms in the
+        # shared RNG lanes and ~12 ms on the device, and ~300 proofs/s need ~30+ proofs in flight.
+        # Measured on one B200 + 16 cores: K = 24 / 32 / 48 -> 249 / 248-278 / 285 proofs/s byte-exact (fast blinding: 295).
+        K = 48
     if K * world > cores:
         os.environ["BPG_BLOCKING_SYNC"] = "1"
     ctx0 = bpg.Context(local)
@@ -314,6 +350,9 @@ def run_ours(args):
         if not args.quick:
             ctx.gens_ensure(1 << 21)
         extras["msm"] = msm_sweep(ctx, sizes)
+
+    if world > 1 and not args.no_extras:
+        extras["msm_sharded"] = msm_sharded_sweep(ctx, dist, local, rank, world, [1 << 20] if args.quick else [1 << 20, 1 << 22])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

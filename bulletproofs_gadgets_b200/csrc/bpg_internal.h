@@ -35,6 +35,7 @@ struct msm_plan {
     msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total;
     const ge_an *tab;   // window tables the point indices refer to (nullptr: the resident generators, ctx->tab)
     uint32_t ptotal;    // points per window of `tab`
+    int lean;           // 1: work-lean bucket reduction (k_msm_rowcol_lean) -- set by the prover / verifier drivers
 };
 
 struct dev_buf { // grow-only device buffer

@@ -287,6 +287,41 @@ __global__ void __launch_bounds__(64) k_msm_rowcol(const ge *__restrict__ bucket
     block_tree_sum_ilp(acc, smem, 64);
     if (t == 0) st_ge(&rc[(size_t)g * (BPG_NROWS + BPG_NCOLS) + idx], acc);
 }
+// Work-lean variant of k_msm_rowcol for the throughput regime (many provers share the GPU, so issue slots matter more than
+// the depth of one reduction): every lane first sums 8 (rows) or ~16 (columns) buckets serially and only the last 5 / 3
+// levels are a tree with idle lanes: ~2 800 warp-level additions per group instead of ~5 000.
+// grid (129 + 64, groups), 32 threads.  Blocks [0,129): row q = blockIdx.x, lane l sums columns l, l+32, ...;
+// blocks [129,193): columns 4 c .. 4 c + 3, lane = (part = lane >> 2, col = lane & 3) sums rows part, part + 8, ...
+__global__ void __launch_bounds__(32) k_msm_rowcol_lean(const ge *__restrict__ buckets, ge *__restrict__ rc) {
+    __shared__ ge smem[32];
+    uint32_t g = blockIdx.y, idx = blockIdx.x, lane = threadIdx.x;
+    const ge *B = buckets + (size_t)g * BPG_NBP;
+    ge acc, o;
+    if (idx < BPG_NROWS) {
+        ld_ge(acc, &B[256u * idx + lane]);
+#pragma unroll 1
+        for (uint32_t k = 1; k < 8; k++) { ld_ge(o, &B[256u * idx + 32u * k + lane]); ge_add_ilp(acc, acc, o); }
+        st_ge(&smem[lane], acc);
+        __syncwarp();
+        for (int s2 = 16; s2 > 0; s2 >>= 1) {
+            if (lane < (uint32_t)s2) { ld_ge(o, &smem[lane + s2]); ge_add_ilp(acc, acc, o); st_ge(&smem[lane], acc); }
+            __syncwarp();
+        }
+        if (lane == 0) st_ge(&rc[(size_t)g * (BPG_NROWS + BPG_NCOLS) + idx], acc);
+    } else {
+        uint32_t part = lane >> 2, col = 4u * (idx - BPG_NROWS) + (lane & 3u);
+        ld_ge(acc, &B[256u * part + col]);
+#pragma unroll 1
+        for (uint32_t q = part + 8; q < BPG_NROWS; q += 8) { ld_ge(o, &B[256u * q + col]); ge_add_ilp(acc, acc, o); }
+        st_ge(&smem[lane], acc);
+        __syncwarp();
+        for (int s2 = 16; s2 >= 4; s2 >>= 1) { // lanes 4 p + c: add the lane 4 (p + s2/4) + c
+            if (lane < (uint32_t)s2) { ld_ge(o, &smem[lane + s2]); ge_add_ilp(acc, acc, o); st_ge(&smem[lane], acc); }
+            __syncwarp();
+        }
+        if (lane < 4) st_ge(&rc[(size_t)g * (BPG_NROWS + BPG_NCOLS) + BPG_NROWS + col], acc);
+    }
+}
 // w * P for a small weight (<= 8 bits), double-and-add from the top bit
 __device__ __forceinline__ void ge_small_mul(ge &r, uint32_t w, const ge &p) {
     ge acc;

@@ -245,7 +245,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     ge *res = (ge *)ctx->results.p;
     uint8_t *d_enc = (uint8_t *)(res + 4);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan);
+    memset(&plan, 0, sizeof plan); plan.lean = 1;
     plan.ngroups = 2;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0, uint32_t g) {
         if (!cnt) return;
@@ -283,7 +283,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
             SYNC_TRY(ctx, s); // raw is released at the end of this scope
         }
     }
-    memset(&plan, 0, sizeof plan);
+    memset(&plan, 0, sizeof plan); plan.lean = 1;
     plan.ngroups = 1;
     add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
     CTX_TRY(msm_run(ctx, s, &plan, res + 2));
@@ -396,7 +396,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_ipp_expand<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
         KCHECK();
-        memset(&plan, 0, sizeof plan);
+        memset(&plan, 0, sizeof plan); plan.lean = 1;
         plan.ngroups = 2;
         plan.tab = tabcur; plan.ptotal = ptcur;
         add_seg(d_sG, Ncur, pG, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // G_i: right half -> L (group 0)
@@ -641,7 +641,7 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
     CUDA_TRY(cudaEventRecord(ctx->ev2, s2));
     const uint32_t pB = (uint32_t)(2 * ctx->cap);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan);
+    memset(&plan, 0, sizeof plan); plan.lean = 1;
     plan.ngroups = 1;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0) {
         msm_seg &sg = plan.seg[plan.nseg++];
