@@ -233,8 +233,8 @@ def run_ours(args):
         # The provers' bulk transcript-RNG draws are batched into SIMD lanes by the library (host_rng_service.h) and the waiting
         # threads sleep, so the prover count is set by latency hiding, not by the core count: a proof spends ~60-100 ms in the
         # shared RNG lanes and ~12 ms on the device, and ~300 proofs/s need ~30+ proofs in flight.
-        # Measured on one B200 + 16 cores: K = 24 / 32 / 48 -> 249 / 248-278 / 285 proofs/s byte-exact (fast blinding: 295).
-        K = 48
+        # Measured on one B200 + 16 cores: K = 24 / 48 / 64 -> 249 / 272 / 297 proofs/s byte-exact (fast blinding: 315).
+        K = 64
     if K * world > cores:
         os.environ["BPG_BLOCKING_SYNC"] = "1"
     ctx0 = bpg.Context(local)
@@ -261,6 +261,8 @@ def run_ours(args):
         for _ in range(steps):
             ln.prove(ext, flags, resident)
 
+    host_cpu_ms = [0.0]
+
     def timed(flags, resident, steps):
         """every prover runs `steps` proofs back to back; no barrier between steps, so one lane's host-side transcript RNG
         overlaps the other lanes' device work.  The region is bracketed by a sync of every context on both sides."""
@@ -268,6 +270,7 @@ def run_ours(args):
             ln.ctx.sync()
         l0 = sum(ln.ctx.launch_count() for ln in lanes)
         ctx.event_record(2)
+        c0 = os.times()
         t0 = time.perf_counter()
         list(pool.map(lambda ln: lane_run(ln, flags, resident, steps), lanes))
         for ln in lanes:
@@ -275,6 +278,8 @@ def run_ours(args):
         ctx.event_record(3)
         ms_dev = ctx.event_elapsed_ms(2, 3)
         wall = (time.perf_counter() - t0) * 1e3
+        c1 = os.times()
+        host_cpu_ms[0] = 1e3 * ((c1.user - c0.user) + (c1.system - c0.system)) / (K * steps)  # this process: all prover threads
         return max(ms_dev, wall), sum(ln.ctx.launch_count() for ln in lanes) - l0
 
     # proofs from every lane are byte-identical (same transcript, same randomness): a cheap cross-context check
@@ -293,6 +298,7 @@ def run_ours(args):
     barrier_max(dist, local, 0.0)
     ms_value, launches = timed(RES, True, args.steps)
     ms_value = barrier_max(dist, local, ms_value)
+    cpu_ms_value = host_cpu_ms[0]
     nl_c, kms_c, pairs_c = ctx.prof_read()   # lane 0's launches inside the timed region: they share the GPU with the other lanes
     ctx.prof_enable(False)
     barrier_max(dist, local, 0.0)
@@ -395,7 +401,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": K * (len(proof) + 32 * inst["m"])},
                 "gpu_launches": int(launches),
                 "proofs_per_sec_fast_blinding": nproofs / (ms_fast * 1e-3),
-                "host_cores": cores,
+                "host_cores": cores, "host_cpu_ms_per_proof": cpu_ms_value,
                 "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "launches": int(nl),
                              "algorithmic_bytes_per_launch": (pairs / nl * 100.0) if nl else None,

@@ -45,6 +45,10 @@ int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s) {
     return BPG_OK;
 }
 #define SYNC_TRY(ctx, s) CTX_TRY(bpg_stream_sync(ctx, s))
+// Device -> pageable host copies return only when the copy is done, and the driver SPINS for everything queued before
+// them (measured: 47 ms of host CPU per proof with 48 provers sharing a GPU, starving the transcript-RNG lanes).  In
+// blocking-sync mode the thread first sleeps on the stream's event, so the copy finds an idle stream.
+#define D2H_TRY(ctx, dst, src, bytes, s) do { if (g_blocking_sync == 1) SYNC_TRY(ctx, s); CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); } while (0)
 
 // ================================================================ context
 extern "C" const char *bpg_strerror(int code) {
@@ -68,6 +72,7 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     CUDA_TRY(cudaSetDevice(device));
     if (bpg_init_constants_host() != 0) return BPG_E_ARG;
     CUDA_TRY(cudaMemcpyToSymbol(c_K, &h_K, sizeof(bpg_consts)));
+    if (g_blocking_sync < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); g_blocking_sync = (e && e[0] == '1') ? 1 : 0; }
     bpg_ctx *ctx = new bpg_ctx();
     ctx->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -125,7 +130,7 @@ extern "C" int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size
 }
 extern "C" int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return BPG_E_ARG;
-    CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, h_dst, d_src, bytes, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
@@ -191,8 +196,8 @@ extern "C" int bpg_gens_export(bpg_ctx *ctx, size_t i0, size_t n, uint8_t *G32, 
     KCHECK();
     k_export_kernel<<<LAUNCH_1D(n, 64), 0, ctx->stream>>>(ctx->tab, (uint32_t)(ctx->cap + i0), (uint32_t)n, d + 32 * n);
     KCHECK();
-    if (G32) CUDA_TRY(cudaMemcpyAsync(G32, d, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (H32) CUDA_TRY(cudaMemcpyAsync(H32, d + 32 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (G32) D2H_TRY(ctx, G32, d, 32 * n, ctx->stream);
+    if (H32) D2H_TRY(ctx, H32, d + 32 * n, 32 * n, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
@@ -204,7 +209,7 @@ extern "C" int bpg_pedersen_gens(bpg_ctx *ctx, uint8_t B32[32], uint8_t Bb32[32]
     k_export_kernel<<<1, 32, 0, ctx->stream>>>(ctx->tab, (uint32_t)(2 * ctx->cap), 2, d);
     KCHECK();
     uint8_t h[64];
-    CUDA_TRY(cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, h, d, 64, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     if (B32) memcpy(B32, h, 32);
     if (Bb32) memcpy(Bb32, h + 32, 32);
@@ -364,7 +369,7 @@ extern "C" int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t
     CUDA_TRY(cudaMemcpyAsync(d + 32 * n, r, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
     k_pedersen_kernel<<<LAUNCH_1D(n, 128), 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
     KCHECK();
-    CUDA_TRY(cudaMemcpyAsync(out32, d + 64 * n, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, out32, d + 64 * n, 32 * n, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
@@ -427,10 +432,10 @@ static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const
     if (out32) {
         uint8_t *d32 = (uint8_t *)(res + 4);
         CTX_TRY(run_compress(ctx, s, final_pt, 1, d32));
-        CUDA_TRY(cudaMemcpyAsync(out32, d32, 32, cudaMemcpyDeviceToHost, s));
+        D2H_TRY(ctx, out32, d32, 32, s);
     }
-    if (out128) CUDA_TRY(cudaMemcpyAsync(out128, final_pt, 128, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    if (out128) D2H_TRY(ctx, out128, final_pt, 128, s);
+    D2H_TRY(ctx, &ok, d_ok, 4, s);
     SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
@@ -457,7 +462,7 @@ extern "C" int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size
     k_points_sum_kernel<<<1, 64, 0, ctx->stream>>>(pts, (uint32_t)n, res);
     KCHECK();
     CTX_TRY(run_compress(ctx, ctx->stream, res, 1, (uint8_t *)(res + 4)));
-    CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, out32, res + 4, 32, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     return BPG_OK;
 }
@@ -477,8 +482,8 @@ extern "C" int bpg_msm(bpg_ctx *ctx, const uint8_t *scalars, const uint8_t *poin
     CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
     CTX_TRY(varbase_msm_dev(ctx, s, d, d + 32 * n, n, res, d_ok, ctx->scratch[3], ctx->scratch[4]));
     CTX_TRY(run_compress(ctx, s, res, 1, (uint8_t *)(res + 4)));
-    CUDA_TRY(cudaMemcpyAsync(out32, res + 4, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, out32, res + 4, 32, s);
+    D2H_TRY(ctx, &ok, d_ok, 4, s);
     SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
@@ -504,8 +509,8 @@ extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t
     k_fold_kernel<<<LAUNCH_1D(n, 64), 0, s>>>((const sc *)d, (const sc *)(d + 32), pts, pts + n, (uint32_t)n, pts + 2 * n);
     KCHECK();
     CTX_TRY(run_compress(ctx, s, pts + 2 * n, n, d + 64));
-    CUDA_TRY(cudaMemcpyAsync(out32, d + 64, 32 * n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, out32, d + 64, 32 * n, s);
+    D2H_TRY(ctx, &ok, d_ok, 4, s);
     SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
 }
@@ -596,7 +601,7 @@ extern "C" int bpg_bench_latency(bpg_ctx *ctx, int iters, double cycles_per_op[8
         KCHECK();
     }
     unsigned long long h[8];
-    CUDA_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, h, d, sizeof h, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     for (int i = 0; i < 8; i++) cycles_per_op[i] = (double)h[i] / iters;
     return BPG_OK;

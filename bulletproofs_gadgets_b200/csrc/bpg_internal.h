@@ -60,6 +60,8 @@ struct bpg_ctx {
     dev_buf batch_gh;         // batch verification: every proof's g | h scalars
     dev_buf mat_pts, mat_ext, mat_tab; // late fold: materialised G^(k) | H^(k), their window chain, their affine-Niels tables
     void *h_pinned = nullptr; size_t h_pinned_cap = 0;
+    std::vector<uint8_t> h_raw; // grow-only host staging of the raw transcript-RNG draws (an 8 MB malloc / free per proof
+                                // means mmap + page faults + munmap under the process-wide mm lock, 48 threads at a time)
     cudaEvent_t tev[16] = {nullptr};
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev; // pairs (start, stop) around k_msm_accumulate

@@ -29,8 +29,8 @@ extern "C" int bpg_mimc_sponge_batch(bpg_ctx *ctx, const uint8_t *blocks, const 
     k_mimc_sponge<<<LAUNCH_1D(n, 128), 0, s>>>((const sc *)din, (const uint32_t *)(din + 32 * nblocks), (uint32_t)n, (sc *)dout,
                                                 trace ? (sc *)(dout + 32 * n) : nullptr);
     KCHECK();
-    CUDA_TRY(cudaMemcpyAsync(out32, dout, 32 * n, cudaMemcpyDeviceToHost, s));
-    if (trace) CUDA_TRY(cudaMemcpyAsync(trace, dout + 32 * n, tbytes, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, out32, dout, 32 * n, s);
+    if (trace) D2H_TRY(ctx, trace, dout + 32 * n, tbytes, s);
     SYNC_TRY(ctx, s);
     return BPG_OK;
 }
@@ -272,7 +272,8 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     } else {
         // The raw 64-byte draws come from the lane-batched RNG service (one Keccak-f per draw, shared SIMD registers with the
         // other provers of this process); Scalar::from_bytes_mod_order_wide happens on the device.
-        std::vector<uint8_t> raw(128 * n + 64);
+        std::vector<uint8_t> &raw = ctx->h_raw;
+        if (raw.size() < 128 * n + 64) raw.resize(128 * n + 64);
         bpgh::RngService::get().draw64(rng, raw.data(), 2 * n);
         tr.mark("rng");
         if (n) {
@@ -280,7 +281,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
             CUDA_TRY(cudaMemcpyAsync(ctx->scratch[12].p, raw.data(), 128 * n, cudaMemcpyHostToDevice, s));
             k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)ctx->scratch[12].p, (uint32_t)n, d_sL, d_sR);
             KCHECK();
-            SYNC_TRY(ctx, s); // raw is released at the end of this scope
+            SYNC_TRY(ctx, s); // the staging buffer is reused by this context's next proof
         }
     }
     memset(&plan, 0, sizeof plan); plan.lean = 1;
@@ -289,7 +290,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CTX_TRY(msm_run(ctx, s, &plan, res + 2));
     CTX_TRY(run_compress(ctx, s, res, 3, d_enc));
     uint8_t AIe[32], AOe[32], Se[32], h_enc[96];
-    CUDA_TRY(cudaMemcpyAsync(h_enc, d_enc, 96, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, h_enc, d_enc, 96, s);
     SYNC_TRY(ctx, s);
     tr.mark("commitMSMs");
     memcpy(AIe, h_enc, 32); memcpy(AOe, h_enc + 32, 32); memcpy(Se, h_enc + 64, 32);
@@ -326,9 +327,9 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_sum_partials<6><<<1, 128, 0, s>>>(d_parts, pb, d_small + 16);
         KCHECK();
-        CUDA_TRY(cudaMemcpyAsync(h_t, d_small + 16, sizeof h_t, cudaMemcpyDeviceToHost, s));
+        D2H_TRY(ctx, h_t, d_small + 16, sizeof h_t, s);
     }
-    if (m) CUDA_TRY(cudaMemcpyAsync(h_wV.data(), d_w + 3 * n, 32 * m, cudaMemcpyDeviceToHost, s));
+    if (m) D2H_TRY(ctx, h_wV.data(), d_w + 3 * n, 32 * m, s);
     SYNC_TRY(ctx, s);
     tr.mark("flatten+poly1");
     sc tb[7];
@@ -405,7 +406,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         add_seg(d_small + 14, 1, pQ, 1);
         CTX_TRY(msm_run(ctx, s, &plan, res));
         CTX_TRY(run_compress(ctx, s, res, 2, d_enc));
-        CUDA_TRY(cudaMemcpyAsync(LR.data() + 64 * j, d_enc, 64, cudaMemcpyDeviceToHost, s));
+        D2H_TRY(ctx, LR.data() + 64 * j, d_enc, 64, s);
         SYNC_TRY(ctx, s);
         t.append("L", LR.data() + 64 * j, 32);
         t.append("R", LR.data() + 64 * j + 32, 32);
@@ -417,8 +418,8 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     }
     tr.mark("ipp");
     sc fab[2];
-    CUDA_TRY(cudaMemcpyAsync(&fab[0], d_a, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&fab[1], d_b, 32, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, &fab[0], d_a, 32, s);
+    D2H_TRY(ctx, &fab[1], d_b, 32, s);
     SYNC_TRY(ctx, s);
 
     // ---- R1CSProof::to_bytes
@@ -654,8 +655,8 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
     KCHECK();
     uint8_t *d_enc = (uint8_t *)(res + 4), enc[32];
     CTX_TRY(run_compress(ctx, s, res + 2, 1, d_enc));
-    CUDA_TRY(cudaMemcpyAsync(enc, d_enc, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, s));
+    D2H_TRY(ctx, enc, d_enc, 32, s);
+    D2H_TRY(ctx, &ok, d_ok, 4, s);
     SYNC_TRY(ctx, s);
     uint8_t nz = 0;
     for (int i = 0; i < 32; i++) nz |= enc[i];
@@ -674,7 +675,7 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     CTX_TRY(verify_prepare(ctx, c, label, label_len, V32, proof, proof_len, ext_rng32, flags, p, nullptr, (sc *)ctx->scratch[7].p));
     if (!p.status) return BPG_OK;
     std::vector<sc> h_slot(c->m + 2);
-    CUDA_TRY(cudaMemcpyAsync(h_slot.data(), p.d_slot, 32 * (c->m + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, h_slot.data(), p.d_slot, 32 * (c->m + 2), ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     verify_complete(p, h_slot.data());
     std::vector<vprep *> S = {&p};
@@ -741,7 +742,7 @@ extern "C" int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *co
         if (preps[i].status) idx.push_back(i);
     }
     std::vector<sc> h_slots(slots + 1);
-    CUDA_TRY(cudaMemcpyAsync(h_slots.data(), d_slots, 32 * slots, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H_TRY(ctx, h_slots.data(), d_slots, 32 * slots, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     for (size_t i : idx) verify_complete(preps[i], h_slots.data() + soff[i]);
     // weights: rho_i = wide_reduce(SHAKE256("bpg batch" || all ext_rng32 || i))  -- unpredictable to the provers
