@@ -22,6 +22,7 @@ SYMBOLS = {
     "bpg_strerror": (C.c_char_p, [_i32]),
     "bpg_launch_count": (C.c_uint64, [_vp]),
     "bpg_sync": (_i32, [_vp]),
+    "bpg_set_blocking_sync": (None, [_i32]),
     "bpg_gens_ensure": (_i32, [_vp, _sz]),
     "bpg_gens_capacity": (_sz, [_vp]),
     "bpg_gens_export": (_i32, [_vp, _sz, _sz, _u8p, _u8p]),
@@ -32,6 +33,8 @@ SYMBOLS = {
     "bpg_msm_gens_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_msm_gens_partial_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_points_sum_compress": (_i32, [_vp, _u8p, _sz, _u8p]),
+    "bpg_msm_gens_partial_to_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "bpg_points_sum_compress_dev": (_i32, [_vp, _vp, _sz, _u8p]),
     "bpg_fold_points": (_i32, [_vp, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]),
     "bpg_mimc_set_constants": (_i32, [_vp, _u8p]),
     "bpg_mimc_hash_batch": (_i32, [_vp, _u8p, _u64p, _sz, _u8p]),

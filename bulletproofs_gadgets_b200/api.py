@@ -104,6 +104,14 @@ class Context:
         self.check(self.lib.bpg_msm_gens_partial_dev(self.h, d_sG, d_sH, n, offset, out))
         return out.raw
 
+    def msm_gens_partial_to_dev(self, d_sG, d_sH, n, offset, d_out128):
+        self.check(self.lib.bpg_msm_gens_partial_to_dev(self.h, d_sG, d_sH, n, offset, d_out128))
+
+    def points_sum_compress_dev(self, d_ext128, n):
+        out = C.create_string_buffer(32)
+        self.check(self.lib.bpg_points_sum_compress_dev(self.h, d_ext128, n, out))
+        return out.raw
+
     def points_sum_compress(self, ext128):
         out = C.create_string_buffer(32)
         self.check(self.lib.bpg_points_sum_compress(self.h, ext128, len(ext128) // 128, out))

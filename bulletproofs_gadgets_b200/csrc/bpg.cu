@@ -44,6 +44,7 @@ int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s) {
     CUDA_TRY(cudaEventSynchronize(ctx->ev));
     return BPG_OK;
 }
+extern "C" void bpg_set_blocking_sync(int on) { g_blocking_sync = on ? 1 : 0; }
 #define SYNC_TRY(ctx, s) CTX_TRY(bpg_stream_sync(ctx, s))
 // Device -> pageable host copies return only when the copy is done, and the driver SPINS for everything queued before
 // them (measured: 47 ms of host CPU per proof with 48 provers sharing a GPU, starving the transcript-RNG lanes).  In
@@ -389,7 +390,7 @@ static int varbase_msm_dev(bpg_ctx *ctx, cudaStream_t s, const uint8_t *d_scalar
 }
 
 static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const uint8_t *h_sG, const uint8_t *h_sH, size_t n, size_t offset,
-                         const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t *out32, uint8_t *out128) {
+                         const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t *out32, uint8_t *out128, void *d_out128 = nullptr) {
     if (!ctx) return BPG_E_ARG;
     if (k && (!extra_scalars || !extra_points32)) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -435,6 +436,7 @@ static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const
         D2H_TRY(ctx, out32, d32, 32, s);
     }
     if (out128) D2H_TRY(ctx, out128, final_pt, 128, s);
+    if (d_out128) CUDA_TRY(cudaMemcpyAsync(d_out128, final_pt, 128, cudaMemcpyDeviceToDevice, s));
     D2H_TRY(ctx, &ok, d_ok, 4, s);
     SYNC_TRY(ctx, s);
     return ok ? BPG_OK : BPG_E_DECOMPRESS;
@@ -451,6 +453,22 @@ extern "C" int bpg_msm_gens_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH
 extern "C" int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out128[128]) {
     if (!out128) return BPG_E_ARG;
     return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n, offset, nullptr, nullptr, 0, nullptr, out128);
+}
+extern "C" int bpg_msm_gens_partial_to_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, void *d_out128) {
+    if (!d_out128) return BPG_E_ARG;
+    return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n, offset, nullptr, nullptr, 0, nullptr, nullptr, d_out128);
+}
+extern "C" int bpg_points_sum_compress_dev(bpg_ctx *ctx, const void *d_ext128, size_t n, uint8_t out32[32]) {
+    if (!ctx || !d_ext128 || !out32 || n == 0 || n > 64) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CTX_TRY(ctx->results.ensure(8 * sizeof(ge) + 64));
+    ge *res = (ge *)ctx->results.p;
+    k_points_sum_kernel<<<1, 64, 0, ctx->stream>>>((const ge *)d_ext128, (uint32_t)n, res);
+    KCHECK();
+    CTX_TRY(run_compress(ctx, ctx->stream, res, 1, (uint8_t *)(res + 4)));
+    D2H_TRY(ctx, out32, res + 4, 32, ctx->stream);
+    SYNC_TRY(ctx, ctx->stream);
+    return BPG_OK;
 }
 extern "C" int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8_t out32[32]) {
     if (!ctx || !ext128 || !out32 || n == 0 || n > 64) return BPG_E_ARG;

@@ -38,9 +38,27 @@ def msm_gens_sharded(ctx, d_sG, d_sH, n, device=None):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(n, rank, world)
+    if world > 1 and device is not None and str(device).startswith("cuda"):
+        # device-resident exchange: the 128-byte partial never leaves HBM; one NCCL all-gather, one 32-byte read-back
+        import ctypes as C
+        bufs = _gather_buffers(world, device)
+        ctx.msm_gens_partial_to_dev(d_sG, d_sH, hi - lo, lo, C.c_void_p(bufs[0].data_ptr()))  # complete on return
+        dist.all_gather_into_tensor(bufs[1], bufs[0])
+        torch.cuda.current_stream(bufs[1].device).synchronize()
+        return ctx.points_sum_compress_dev(C.c_void_p(bufs[1].data_ptr()), world)
     part = ctx.msm_gens_partial_dev(d_sG, d_sH, hi - lo, lo)
     parts = allgather_bytes(part, device)
     return ctx.points_sum_compress(b"".join(parts))
+
+
+_GATHER = {}
+
+
+def _gather_buffers(world, device):
+    key = (world, str(device))
+    if key not in _GATHER:
+        _GATHER[key] = (torch.zeros(128, dtype=torch.uint8, device=device), torch.zeros(128 * world, dtype=torch.uint8, device=device))
+    return _GATHER[key]
 
 
 def gather_verdicts(local, n_total, device=None):

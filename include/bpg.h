@@ -53,6 +53,9 @@ const char *bpg_strerror(int code);
 /* kernels launched by this context so far (bench.py reports the delta as gpu_launches) */
 uint64_t bpg_launch_count(bpg_ctx *ctx);
 int bpg_sync(bpg_ctx *ctx);
+/* How host threads wait for the device (process-wide; initial value from the environment, BPG_BLOCKING_SYNC=1):
+ * 0 = spin (lowest latency for one caller), 1 = sleep on an event (many provers per GPU: leaves the cores to the transcript RNG) */
+void bpg_set_blocking_sync(int on);
 
 /* BulletproofGens::new(capacity, 1) + PedersenGens::default()  [ext; prover.rs:53,92  verifier.rs:89].
  * Derives the G/H chains (SHAKE256 stream on the host, double-Elligator on the device) and builds the resident
@@ -79,6 +82,11 @@ int bpg_msm_gens_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n,
 /* partial sum as an uncompressed extended point (128 B) for multi-GPU point-range splits, and the combiner */
 int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out128[128]);
 int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8_t out32[32]);
+/* the same two steps with the 128-byte partial points staying on the device, for callers whose collective runs there
+ * (NCCL all-gather of the partials through torch.distributed): the partial is written to d_out128 (complete when the
+ * call returns), and the sum reads n gathered partials from d_ext128 (the caller orders it after its collective) */
+int bpg_msm_gens_partial_to_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, void *d_out128);
+int bpg_points_sum_compress_dev(bpg_ctx *ctx, const void *d_ext128, size_t n, uint8_t out32[32]);
 
 /* One inner-product-argument generator fold: out[i] = sl*PL[i] + sr*PR[i]  (InnerProductProof::create's
  * G'/H' update, dalek: a 2-point vartime MSM per element) [ext; inside prover.rs:93]. */
