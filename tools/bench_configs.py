@@ -63,9 +63,9 @@ def main():
         fe.prover_main(stem, seed=1, ctx=ctx, label="example")
         t_p, nc = timed(lambda: fe.prover_main(stem, seed=1, ctx=ctx, label="example"), 2)
         t_v, ok = timed(lambda: fe.verifier_main(stem, ctx=ctx, label="example"), 2)
-        run = fe.ProverRun(b"example", open(stem + ".gadgets").read(), open(stem + ".inst").read(), open(stem + ".wtns").read(), seed=1, ctx=ctx)
-        t_dev, _ = timed(lambda: run.prover.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32)), 2)
-        res["config0_example_cli"] = {"constraints": nc, "multipliers": run.prover.get_num_multiplications(), "prover_cli_ms_incl_python_frontend": t_p,
+        prun = fe.ProverRun(b"example", open(stem + ".gadgets").read(), open(stem + ".inst").read(), open(stem + ".wtns").read(), seed=1, ctx=ctx)
+        t_dev, _ = timed(lambda: prun.prover.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32)), 2)
+        res["config0_example_cli"] = {"constraints": nc, "multipliers": prun.prover.get_num_multiplications(), "prover_cli_ms_incl_python_frontend": t_p,
                                       "verifier_cli_ms_incl_python_frontend": t_v, "prove_call_ms": t_dev, "verifier_prints": "true" if ok else "false"}
     if "3" in which:
         t0 = time.perf_counter()
