@@ -402,7 +402,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "n_multipliers": n, "padded_n": GENS_CAP, "commitments": inst["m"],
                            "constraints": int(len(inst["csr"][0]) - 1), "proofs_per_step_per_gpu": K,
                            "concurrency": "%d independent provers per GPU (one host thread + one bpg_ctx each); a step is one proof per prover" % K,
-                           "l2": "window tables (201 MB per context at 2^16 capacity) exceed the 126 MB L2", "byte_exact": True},
+                           "l2": "window tables (201 MB at 2^16 capacity, one set per GPU shared by all provers) exceed the 126 MB L2", "byte_exact": True},
                 "e2e": {"value": nproofs / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": K * (3 * 32 * n + 2 * 32 * inst["m"] + 64 * n),
                         "d2h_bytes_per_step": K * (len(proof) + 32 * inst["m"])},
                 "gpu_launches": int(launches),

@@ -94,8 +94,8 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     ctx->prof_ev.clear();
     DSTEP("prof events destroyed");
-    if (ctx->tab) cudaFree(ctx->tab);
-    if (ctx->comb) cudaFree(ctx->comb);
+    ctx->gens.reset(); // the tables are freed with their last user
+    ctx->tab = nullptr; ctx->comb = nullptr;
     DSTEP("tables freed");
     dev_buf *bufs[] = {&ctx->counts, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->partial, &ctx->buckets, &ctx->lvlP, &ctx->lvlQ, &ctx->heavy, &ctx->results};
     for (dev_buf *b : bufs) b->release();
@@ -142,18 +142,22 @@ static const uint8_t RISTRETTO_BASEPOINT[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0x
 
 extern "C" size_t bpg_gens_capacity(bpg_ctx *ctx) { return ctx ? ctx->cap : 0; }
 
-extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
-    if (!ctx) return BPG_E_ARG;
-    if (capacity <= ctx->cap) return BPG_OK;
-    if (capacity > (1u << 22)) return BPG_E_SIZE;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    size_t cap = 64;
-    while (cap < capacity) cap <<= 1;
-    if (ctx->tab) { cudaFree(ctx->tab); ctx->tab = nullptr; }
+gens_tables::~gens_tables() {
+    cudaSetDevice(device);
+    if (tab) cudaFree(tab);
+    if (comb) cudaFree(comb);
+}
+#include <mutex>
+static std::mutex g_gens_mu;
+static std::weak_ptr<gens_tables> g_gens[64]; // per device: the largest table set currently alive
+
+static int gens_build(bpg_ctx *ctx, size_t cap, std::shared_ptr<gens_tables> &out) {
+    std::shared_ptr<gens_tables> g = std::make_shared<gens_tables>();
+    g->device = ctx->device;
     uint32_t ptotal = (uint32_t)(2 * cap + 2);
     size_t tab_bytes = (size_t)BPG_NWIN * ptotal * sizeof(ge_an);
-    if (cudaMalloc((void **)&ctx->tab, tab_bytes) != cudaSuccess) { cudaGetLastError(); return BPG_E_NOMEM; }
-    if (!ctx->comb) CUDA_TRY(cudaMalloc((void **)&ctx->comb, (size_t)2 * 32 * 128 * sizeof(ge_an)));
+    if (cudaMalloc((void **)&g->tab, tab_bytes) != cudaSuccess) { cudaGetLastError(); return BPG_E_NOMEM; }
+    CUDA_TRY(cudaMalloc((void **)&g->comb, (size_t)2 * 32 * 128 * sizeof(ge_an)));
     // SHAKE256 streams on two host threads (sequential squeeze, ~0.3 us per 136 bytes)
     size_t sbytes = 64 * cap;
     // pageable staging: this is a one-off upload, and freeing / re-allocating a large pinned buffer after timing events had
@@ -169,20 +173,49 @@ extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
     CTX_TRY(ctx->scratch[0].ensure(2 * sbytes + 128));
     uint8_t *ds = (uint8_t *)ctx->scratch[0].p;
     CUDA_TRY(cudaMemcpyAsync(ds, hs, 2 * sbytes + 128, cudaMemcpyHostToDevice, ctx->stream));
-    k_gens_tables<<<LAUNCH_1D(2 * cap, 128), 0, ctx->stream>>>(ds, (uint32_t)(2 * cap), 0, ptotal, ctx->tab);
+    k_gens_tables<<<LAUNCH_1D(2 * cap, 128), 0, ctx->stream>>>(ds, (uint32_t)(2 * cap), 0, ptotal, g->tab);
     KCHECK();
     CTX_TRY(ctx->scratch[1].ensure(16));
     uint32_t one = 1;
     CUDA_TRY(cudaMemcpyAsync(ctx->scratch[1].p, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_point_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes + 64, 1, (uint32_t)(2 * cap), ptotal, ctx->tab, (uint32_t *)ctx->scratch[1].p);
+    k_point_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes + 64, 1, (uint32_t)(2 * cap), ptotal, g->tab, (uint32_t *)ctx->scratch[1].p);
     KCHECK();
-    k_gens_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes, 1, (uint32_t)(2 * cap + 1), ptotal, ctx->tab);
+    k_gens_tables<<<1, 32, 0, ctx->stream>>>(ds + 2 * sbytes, 1, (uint32_t)(2 * cap + 1), ptotal, g->tab);
     KCHECK();
-    k_build_comb<<<1, 64, 0, ctx->stream>>>(ctx->tab, ptotal, (uint32_t)(2 * cap), ctx->comb);
+    k_build_comb<<<1, 64, 0, ctx->stream>>>(g->tab, ptotal, (uint32_t)(2 * cap), g->comb);
     KCHECK();
-    SYNC_TRY(ctx, ctx->stream);
-    ctx->cap = cap;
-    ctx->ptotal = ptotal;
+    SYNC_TRY(ctx, ctx->stream); // complete before any other context (other stream) can see the tables
+    g->cap = cap;
+    g->ptotal = ptotal;
+    out = g;
+    return BPG_OK;
+}
+
+extern "C" int bpg_gens_ensure(bpg_ctx *ctx, size_t capacity) {
+    if (!ctx) return BPG_E_ARG;
+    if (capacity <= ctx->cap) return BPG_OK;
+    if (capacity > (1u << 22)) return BPG_E_SIZE;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    size_t cap = 64;
+    while (cap < capacity) cap <<= 1;
+    static int private_tables = -1;
+    if (private_tables < 0) { const char *e = getenv("BPG_PRIVATE_TABLES"); private_tables = (e && e[0] == '1') ? 1 : 0; }
+    std::shared_ptr<gens_tables> g;
+    {
+        // held while building: contexts asking for the same tables at the same time wait for the first one instead of
+        // building their own copy
+        std::lock_guard<std::mutex> lk(g_gens_mu);
+        if (!private_tables && ctx->device < 64) g = g_gens[ctx->device].lock();
+        if (!g || g->cap < cap) {
+            g.reset();
+            CTX_TRY(gens_build(ctx, cap, g));
+            if (!private_tables && ctx->device < 64) g_gens[ctx->device] = g;
+        }
+    }
+    SYNC_TRY(ctx, ctx->stream); // nothing of this context may still read the tables it is about to release
+    ctx->gens = g;
+    ctx->tab = g->tab; ctx->comb = g->comb;
+    ctx->cap = g->cap; ctx->ptotal = g->ptotal;
     return BPG_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,17 @@ struct dev_buf { // grow-only device buffer
     void release();
 };
 
+// Window tables of the generators of one device: built once, shared by every context of the process on that device
+// (BulletproofGens is a deterministic function of the capacity).  One 201 MB table set at 2^16 instead of one per prover
+// thread also lets the 126 MB L2 hold most of what the accumulate kernel gathers.
+struct gens_tables {
+    int device = 0;
+    size_t cap = 0;
+    uint32_t ptotal = 0;
+    ge_an *tab = nullptr, *comb = nullptr;
+    ~gens_tables();
+};
+
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -51,6 +63,7 @@ struct bpg_ctx {
     // resident generators
     size_t cap = 0;           // per-chain capacity (power of two); tables cover 2*cap+2 points
     uint32_t ptotal = 0;
+    std::shared_ptr<gens_tables> gens; // owner of tab / comb below (shared between contexts unless BPG_PRIVATE_TABLES=1)
     ge_an *tab = nullptr;     // [BPG_NWIN][ptotal]
     ge_an *comb = nullptr;    // [2][32][128] signed 8-bit comb for B and B~ (Pedersen commits)
     // MSM workspace

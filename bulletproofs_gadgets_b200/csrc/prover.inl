@@ -371,7 +371,9 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     // n' = N >> k0 folded generators are materialised and the remaining rounds run over them (EG = EH = 1 again).
     int k0 = lgN; // no late fold
     bool late = (flags & BPG_FLAG_FORCE_LATE_FOLD) ? lgN >= 2 : (!(flags & BPG_FLAG_NO_LATE_FOLD) && lgN >= 15);
-    if (late) k0 = std::max(1, lgN - 9);
+    static int late_lg = -1; // log2 of the number of folded generators kept per vector (512 measured best: see DESIGN.md)
+    if (late_lg < 0) { const char *e = getenv("BPG_LATE_FOLD_LG"); late_lg = e ? atoi(e) : 9; if (late_lg < 1 || late_lg > 12) late_lg = 9; }
+    if (late) k0 = std::max(1, lgN - late_lg);
     size_t Ncur = N;                       // generators of the current basis
     uint32_t pG = 0, pH = (uint32_t)ctx->cap, pQ = pB; // point indices of G_0, H_0 and B in the current tables
     const ge_an *tabcur = nullptr;
