@@ -342,7 +342,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
             if (scatter) k_msm_digits<1, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
             else k_msm_digits<0, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
         }));
-        k_mat_reduce<<<G, 32, 0, s>>>((const ge *)ctx->buckets.p, (uint32_t)G, d_out);
+        k_small_reduce<<<G, 256, 0, s>>>((const ge *)ctx->buckets.p, d_out);
         KCHECK();
         return BPG_OK;
     }
@@ -401,7 +401,10 @@ extern "C" int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t
     uint8_t *d = (uint8_t *)ctx->scratch[0].p;
     CUDA_TRY(cudaMemcpyAsync(d, v, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d + 32 * n, r, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
-    k_pedersen_kernel<<<LAUNCH_1D(n, 128), 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
+    if (n <= 512) // few commitments: one warp each (latency); many: one thread each (throughput)
+        k_pedersen_warp<<<(unsigned)n, 32, 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
+    else
+        k_pedersen_kernel<<<LAUNCH_1D(n, 128), 0, ctx->stream>>>((const sc *)d, (const sc *)(d + 32 * n), (uint32_t)n, ctx->comb, d + 64 * n, nullptr);
     KCHECK();
     D2H_TRY(ctx, out32, d + 64 * n, 32 * n, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);

@@ -204,6 +204,57 @@ __global__ void __launch_bounds__(128) k_pedersen_kernel(const sc *__restrict__ 
     }
 }
 
+// Same commitment, one warp each, for the handful of commitments inside a proof (V_1..V_m, T_1..T_6: nothing else of the proof
+// can proceed until they are in the transcript): lane w adds the comb entries of byte w of both scalars, a 5-level tree sums
+// the lanes, lane 0 encodes.  Depth 2 + 5 point additions instead of 64.
+__global__ void __launch_bounds__(32) k_pedersen_warp(const sc *__restrict__ v, const sc *__restrict__ r, uint32_t n, const ge_an *__restrict__ comb,
+                                                       uint8_t *__restrict__ out32, ge *__restrict__ out_ext) {
+    __shared__ ge smem[32];
+    uint32_t i = blockIdx.x, lane = threadIdx.x;
+    if (i >= n) return;
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int b = 0; b < 2; b++) {
+        sc k;
+        ld_sc(k, b == 0 ? &v[i] : &r[i]);
+        sc_reduce(k, k);
+        int carry = 0, dw = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            int by = (int)((k.v[j >> 2] >> (8 * (j & 3))) & 0xFF) + carry;
+            carry = by >= 128;
+            if (j == (int)lane) dw = by - (carry << 8);
+        }
+        if (dw != 0) {
+            int mag = dw < 0 ? -dw : dw;
+            ge_an a, na;
+            ld_an(a, &comb[((size_t)b * 32 + lane) * 128 + (mag - 1)]);
+            if (dw < 0) { ge_an_neg(na, a); a = na; }
+            ge_add_an(acc, acc, a);
+        }
+    }
+    st_ge(&smem[lane], acc);
+    __syncwarp();
+    for (int s2 = 16; s2 > 0; s2 >>= 1) {
+        if (lane < (uint32_t)s2) {
+            ge o;
+            ld_ge(o, &smem[lane + s2]);
+            ge_add(acc, acc, o);
+            st_ge(&smem[lane], acc);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (out_ext) st_ge(&out_ext[i], acc);
+        if (out32) {
+            uint8_t e[32];
+            ristretto_encode(e, acc);
+            for (int q = 0; q < 32; q++) out32[32ull * i + q] = e[q];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- small variable-base MSM (verifier extras, bpg_msm, fold)
 // one thread per term: 4-bit fixed-window scalar multiplication (table of 8 multiples in local memory), then a
 // block tree reduction; block results are summed by a second launch of k_points_sum_kernel.

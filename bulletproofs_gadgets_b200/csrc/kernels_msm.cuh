@@ -473,6 +473,43 @@ __global__ void __launch_bounds__(32) k_mat_reduce(const ge *__restrict__ bucket
         st_ge(&out[o], lo);
     }
 }
+// Latency-lean reduction of the same 2 x 129 bucket layout for the few groups of a SMALL MSM (late IPP rounds: 2 groups,
+// nothing else of this proof can run until L_j, R_j are known).  One 256-thread block per group, thread = (set, b - 1):
+// b * T_b by a fixed 8-step double-and-add (uniform across the warp), block-wide tree, then low + 2^8 high.
+// Depth ~ 16 + 8 + 9 point operations instead of ~ 55 in k_mat_reduce, at ~ 3x its work (irrelevant for 2 groups; the
+// late-fold materialisation with its 1024 outputs keeps the work-lean kernel).
+__global__ void __launch_bounds__(256) k_small_reduce(const ge *__restrict__ buckets, ge *__restrict__ out) {
+    __shared__ ge smem[256];
+    uint32_t g = blockIdx.x, t = threadIdx.x;
+    uint32_t set = t >> 7, b = (t & 127u) + 1u;
+    ge p, acc;
+    ld_ge(p, &buckets[((size_t)2 * g + set) * BPG_MAT_NB + b]);
+    ge_identity(acc);
+#pragma unroll 1
+    for (int k = 7; k >= 0; k--) {
+        ge_dbl_ilp(acc, acc);
+        if ((b >> k) & 1u) ge_add_ilp(acc, acc, p);
+    }
+    st_ge(&smem[t], acc);
+    __syncthreads();
+    for (int s2 = 64; s2 > 0; s2 >>= 1) { // two independent trees: threads [0,128) and [128,256)
+        if ((t & 127u) < (uint32_t)s2) {
+            ge o;
+            ld_ge(o, &smem[t + s2]);
+            ge_add_ilp(acc, acc, o);
+            st_ge(&smem[t], acc);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        ge hi;
+        ld_ge(hi, &smem[128]);
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) ge_dbl_ilp(hi, hi);
+        ge_add_ilp(acc, acc, hi);
+        st_ge(&out[g], acc);
+    }
+}
 // window chain of the materialised points: ext[w][q] = 2^(16 w) P_q  (one thread per point, 240 doublings)
 __global__ void __launch_bounds__(64) k_mat_chain(const ge *__restrict__ pts, uint32_t npts, ge *__restrict__ ext) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;

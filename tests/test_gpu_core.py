@@ -46,6 +46,10 @@ def test_pedersen_commit_matches_oracle(ctx):
     assert ctx.pedersen_commit(v, r) == ol.pedersen_commit(v, r)
     z = bytes(32)
     assert ctx.pedersen_commit(z, z) == bytes(32)
+    # > 512 commitments: the one-thread-per-commitment kernel (<= 512 use one warp each)
+    big = [rs(rnd) for _ in range(700)] + [e.to_bytes(32, "little") for e in edge]
+    v, r = b"".join(big), b"".join(reversed(big))
+    assert ctx.pedersen_commit(v, r) == ol.pedersen_commit(v, r)
 
 
 @pytest.mark.parametrize("n,dist", [(1, "uniform"), (2, "uniform"), (63, "uniform"), (64, "uniform"), (65, "uniform"), (1000, "uniform"),
