@@ -256,21 +256,31 @@ def run_ours(args):
         outs = list(pool.map(lambda ln: ln.prove(ext, flags, resident), lanes))
         return outs
 
+    tickets = {"next": 0, "total": 0, "lock": threading.Lock()}
+
     def lane_run(ln, flags, resident, steps):
-        # staggered start (inside the timed region): lane i begins i * 3 ms late so that the lanes' host-RNG and device
-        # phases interleave from the first proof on instead of all lanes hitting the CPU, then the GPU, in lockstep
-        time.sleep(0.003 * lanes.index(ln))
-        for _ in range(steps):
+        # staggered start (inside the timed region): lane i begins i ms late so that the lanes' host-RNG and device phases
+        # interleave from the first proof on instead of all lanes hitting the CPU, then the GPU, in lockstep.
+        # The K * steps proofs of the region are handed out one at a time, so every lane stays busy until the last proofs
+        # are taken and the region does not end on a few straggling lanes.
+        time.sleep(0.001 * lanes.index(ln))
+        while True:
+            with tickets["lock"]:
+                if tickets["next"] >= tickets["total"]:
+                    return
+                tickets["next"] += 1
             ln.prove(ext, flags, resident)
 
     host_cpu_ms = [0.0]
 
     def timed(flags, resident, steps):
-        """every prover runs `steps` proofs back to back; no barrier between steps, so one lane's host-side transcript RNG
-        overlaps the other lanes' device work.  The region is bracketed by a sync of every context on both sides."""
+        """K * steps proofs (`steps` per prover on average), the provers free-running with no barrier between steps, so one
+        lane's host-side transcript RNG overlaps the other lanes' device work.  The region is bracketed by a sync of every
+        context on both sides."""
         for ln in lanes:
             ln.ctx.sync()
         l0 = sum(ln.ctx.launch_count() for ln in lanes)
+        tickets["next"], tickets["total"] = 0, K * steps
         ctx.event_record(2)
         c0 = os.times()
         t0 = time.perf_counter()
@@ -441,7 +451,7 @@ def main():
         os.write(saved, (text + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--provers", type=int, default=0, help="concurrent provers (host threads / contexts) per GPU; 0 = auto")

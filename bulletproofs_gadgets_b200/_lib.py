@@ -23,6 +23,7 @@ SYMBOLS = {
     "bpg_launch_count": (C.c_uint64, [_vp]),
     "bpg_sync": (_i32, [_vp]),
     "bpg_set_blocking_sync": (None, [_i32]),
+    "bpg_set_sizing_mode": (None, [_i32]),
     "bpg_gens_ensure": (_i32, [_vp, _sz]),
     "bpg_gens_capacity": (_sz, [_vp]),
     "bpg_gens_export": (_i32, [_vp, _sz, _sz, _u8p, _u8p]),

@@ -273,16 +273,34 @@ static int run_points_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, size_t n, ge 
     return BPG_OK;
 }
 
+// Protocol calls in flight in this process.  With several provers / verifiers sharing the GPU the kernels are sized for
+// work efficiency (long accumulate chunks: fewer bucket runs cut at chunk borders, measured +5 % proofs/s at half a wave;
+// work-lean row/column reduction); a lone caller gets the latency-oriented sizes (two waves, shallow reductions).
+#include <atomic>
+static std::atomic<int> g_inflight{0};
+struct bpg_inflight_guard {
+    bpg_inflight_guard() { g_inflight.fetch_add(1, std::memory_order_relaxed); }
+    ~bpg_inflight_guard() { g_inflight.fetch_sub(1, std::memory_order_relaxed); }
+};
+static std::atomic<int> g_sizing_mode{-1}; // -1 auto, 0 latency, 1 throughput (bpg_set_sizing_mode)
+extern "C" void bpg_set_sizing_mode(int mode) { g_sizing_mode.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
+static inline int bpg_lean_now() {
+    int m = g_sizing_mode.load(std::memory_order_relaxed);
+    return m >= 0 ? m : (g_inflight.load(std::memory_order_relaxed) >= 4 ? 1 : 0);
+}
+
 // Common front half of every bucket MSM: histogram -> scan -> counting-sort scatter -> chunked accumulation -> per-bucket
 // finish.  `digits(scatter, counters_or_cursor, sorted)` launches the recoding kernel of the caller (k_msm_digits for plain
 // MSMs, k_mat_digits for the multi-output fold).  Leaves the nb bucket sums in ctx->buckets.
 template <class DigitsLaunch>
-static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpairs, bool any, const ge_an *tab, DigitsLaunch &&digits) {
-    // chunk = sorted pairs summed by one thread: sized so that the accumulate grid has >= ~8 warps per SM sub-partition
-    // (two full waves of 4 blocks x 128 threads on 148 SMs = 151 552 threads)
-    uint32_t CH = (uint32_t)((maxpairs + 151551) / 151552);
+static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpairs, bool any, const ge_an *tab, int lean, DigitsLaunch &&digits) {
+    // chunk = sorted pairs summed by one thread.  Latency sizing: two full waves of 4 blocks x 128 threads on 148 SMs
+    // (151 552 threads).  Throughput sizing (lean): half a wave of longer chunks -- other proofs fill the rest of the GPU.
+    size_t tgt = lean ? 37888 : 151552;
+    uint32_t cap = lean ? 2 * BPG_CHUNK : BPG_CHUNK;
+    uint32_t CH = (uint32_t)((maxpairs + tgt - 1) / tgt);
     if (CH < 8) CH = 8;
-    if (CH > BPG_CHUNK) CH = BPG_CHUNK;
+    if (CH > cap) CH = cap;
     size_t nchunks = (maxpairs + CH - 1) / CH + 1;
     uint32_t ntiles = (nb + 1023) / 1024;
     CTX_TRY(ctx->counts.ensure(((size_t)nb + 2 + ntiles + 2) * 4)); // counters, then the scan's ticket + per-tile totals
@@ -338,7 +356,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
         // would cost more than the accumulation.  Split every 16-bit digit into two 8-bit digits instead (two pairs per
         // digit, 2 x 129 buckets per group) and reduce each group with one k_mat_reduce block.
         uint32_t nb = (uint32_t)G * 2u * BPG_MAT_NB;
-        CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN * 2, total != 0, tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+        CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN * 2, total != 0, tab, plan->lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
             if (scatter) k_msm_digits<1, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
             else k_msm_digits<0, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
         }));
@@ -349,7 +367,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     uint32_t nb = (uint32_t)G * BPG_NBP;
     CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
     CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
-    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN, total != 0, tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN, total != 0, tab, plan->lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
         if (scatter) k_msm_digits<1, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
         else k_msm_digits<0, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
     }));
@@ -369,7 +387,7 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
 
 // Late fold (see kernels_msm.cuh): G^(k)_i, H^(k)_i for i < n' from the per-generator factors EG, EH (length N), then the
 // 16-window affine-Niels tables of those 2 n' points (+ B) in ctx->mat_tab with 2 n' + 2 points per window.
-int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH) {
+int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean) {
     uint32_t nout = 2 * nprime;
     uint32_t nb = 2 * nout * BPG_MAT_NB;
     uint32_t pt_small = nout + 2;
@@ -377,7 +395,7 @@ int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t npri
     CTX_TRY(ctx->mat_ext.ensure((size_t)BPG_NWIN * nout * sizeof(ge)));
     CTX_TRY(ctx->mat_tab.ensure((size_t)BPG_NWIN * pt_small * sizeof(ge_an)));
     uint32_t cap = (uint32_t)ctx->cap, ptotal = ctx->ptotal;
-    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)2 * N * BPG_NWIN * 2, true, ctx->tab, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)2 * N * BPG_NWIN * 2, true, ctx->tab, lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
         if (scatter) k_mat_digits<1><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
         else k_mat_digits<0><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
     }));

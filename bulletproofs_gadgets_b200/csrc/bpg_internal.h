@@ -36,7 +36,8 @@ struct msm_plan {
     msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total;
     const ge_an *tab;   // window tables the point indices refer to (nullptr: the resident generators, ctx->tab)
     uint32_t ptotal;    // points per window of `tab`
-    int lean;           // 1: work-lean bucket reduction (k_msm_rowcol_lean) -- set by the prover / verifier drivers
+    int lean;           // 1: throughput sizing (long accumulate chunks, k_msm_rowcol_lean) -- set by the protocol drivers when
+                        //    several proofs are in flight in this process (bpg_lean_now)
 };
 
 struct dev_buf { // grow-only device buffer
@@ -88,4 +89,4 @@ struct bpg_ctx {
 int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s);
 int msm_run(bpg_ctx *c, cudaStream_t s, msm_plan *plan, ge *d_out /* ngroups extended points */);
 // late fold (kernels_msm.cuh): tables of the 2 n' folded generators (+ B at index 2 n') into ctx->mat_tab, ptotal = 2 n' + 2
-int msm_materialise_fold(bpg_ctx *c, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH);
+int msm_materialise_fold(bpg_ctx *c, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean);

@@ -196,6 +196,7 @@ struct phase_trace {
 extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *aL, const uint8_t *aR,
                                const uint8_t *aO, const uint8_t *v, const uint8_t *v_blinding, const uint8_t ext_rng32[32], unsigned flags,
                                uint8_t *V_out, uint8_t *proof, size_t proof_cap) {
+    bpg_inflight_guard inflight_;
     if (!ctx || !c || !label || !ext_rng32 || !proof) return BPG_E_ARG;
     size_t n = c->n, m = c->m;
     if ((n && (!aL || !aR || !aO)) || (m && (!v || !v_blinding))) return BPG_E_ARG;
@@ -245,7 +246,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     ge *res = (ge *)ctx->results.p;
     uint8_t *d_enc = (uint8_t *)(res + 4);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan); plan.lean = 1;
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
     plan.ngroups = 2;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0, uint32_t g) {
         if (!cnt) return;
@@ -284,7 +285,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
             SYNC_TRY(ctx, s); // the staging buffer is reused by this context's next proof
         }
     }
-    memset(&plan, 0, sizeof plan); plan.lean = 1;
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
     plan.ngroups = 1;
     add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
     CTX_TRY(msm_run(ctx, s, &plan, res + 2));
@@ -381,7 +382,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     for (int j = 0; j < lgN; j++) {
         uint32_t nj = (uint32_t)(N >> j), h = nj >> 1;
         if (j == k0) {
-            CTX_TRY(msm_materialise_fold(ctx, s, (uint32_t)N, nj, d_EG, d_EH));
+            CTX_TRY(msm_materialise_fold(ctx, s, (uint32_t)N, nj, d_EG, d_EH, bpg_lean_now()));
             Ncur = nj;
             tabcur = (const ge_an *)ctx->mat_tab.p; ptcur = 2 * nj + 2;
             pG = 0; pH = nj; pQ = 2 * nj;
@@ -399,7 +400,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_ipp_expand<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
         KCHECK();
-        memset(&plan, 0, sizeof plan); plan.lean = 1;
+        memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
         plan.ngroups = 2;
         plan.tab = tabcur; plan.ptotal = ptcur;
         add_seg(d_sG, Ncur, pG, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // G_i: right half -> L (group 0)
@@ -644,7 +645,7 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
     CUDA_TRY(cudaEventRecord(ctx->ev2, s2));
     const uint32_t pB = (uint32_t)(2 * ctx->cap);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan); plan.lean = 1;
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
     plan.ngroups = 1;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0) {
         msm_seg &sg = plan.seg[plan.nseg++];
@@ -668,6 +669,7 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
 
 extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32, const uint8_t *proof,
                                size_t proof_len, const uint8_t ext_rng32[32], unsigned flags, int *accept) {
+    bpg_inflight_guard inflight_;
     if (!accept) return BPG_E_ARG;
     *accept = 0;
     if (c && c->m && !V32) return BPG_E_ARG;
@@ -719,6 +721,7 @@ static int verify_bisect(bpg_ctx *ctx, std::vector<vprep> &preps, const std::vec
 extern "C" int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *const *circuits, const uint8_t *const *labels, const size_t *label_lens,
                                      const uint8_t *const *V32, const uint8_t *const *proofs, const size_t *proof_lens, const uint8_t *ext_rng32,
                                      unsigned flags, int *accept) {
+    bpg_inflight_guard inflight_;
     if (!ctx || (count && (!circuits || !labels || !label_lens || !V32 || !proofs || !proof_lens || !ext_rng32 || !accept))) return BPG_E_ARG;
     if (!count) return BPG_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));

@@ -56,6 +56,11 @@ int bpg_sync(bpg_ctx *ctx);
 /* How host threads wait for the device (process-wide; initial value from the environment, BPG_BLOCKING_SYNC=1):
  * 0 = spin (lowest latency for one caller), 1 = sleep on an event (many provers per GPU: leaves the cores to the transcript RNG) */
 void bpg_set_blocking_sync(int on);
+/* Kernel sizing of the protocol calls (process-wide): -1 = automatic (throughput sizing while >= 4 prove / verify calls are
+ * in flight in this process, latency sizing otherwise), 0 = latency (two-wave accumulate grids, shallow bucket reductions),
+ * 1 = throughput (half-wave grids of long chunks, work-lean reductions; for several processes sharing one GPU).
+ * Results are identical in every mode. */
+void bpg_set_sizing_mode(int mode);
 
 /* BulletproofGens::new(capacity, 1) + PedersenGens::default()  [ext; prover.rs:53,92  verifier.rs:89].
  * Derives the G/H chains (SHAKE256 stream on the host, double-Elligator on the device) and builds the resident

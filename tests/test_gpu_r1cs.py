@@ -178,3 +178,48 @@ def test_late_fold_proof_bytes_match_oracle(ctx, nmul, seed):
     assert forced == want
     assert plain == want
     assert gpu_verify(ctx, inst, V1, forced)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sizing_modes_give_identical_proofs(ctx, mode):
+    """latency vs throughput kernel sizing (bpg_set_sizing_mode: accumulate chunk length, row/column reduction variant) must not
+    change a single byte; sizes chosen so that the commitment MSMs and the first IPP rounds take the 2^15-bucket path"""
+    import bulletproofs_gadgets_b200._lib as lb
+    inst = circuits.chain_instance(1500, 77)
+    ext = bytes(range(3, 35))
+    want, Vw = oracle_prove(inst, 2048, ext)
+    ctx.lib.bpg_set_sizing_mode(mode)
+    try:
+        got, V = gpu_prove(ctx, inst, ext)
+        forced, _ = gpu_prove(ctx, inst, ext, lb.FLAG_FORCE_LATE_FOLD)
+        assert gpu_verify(ctx, inst, V, got)
+    finally:
+        ctx.lib.bpg_set_sizing_mode(-1)
+    assert V == Vw and got == want and forced == want
+
+
+def test_concurrent_provers_match_oracle():
+    """eight provers (own context each) in eight host threads: shared generator tables, shared transcript-RNG lanes, automatic
+    throughput sizing -- every proof byte-identical to the oracle's"""
+    import threading
+    import bulletproofs_gadgets_b200 as bpg
+    inst = circuits.chain_instance(700, 31)
+    want, Vw = oracle_prove(inst, 2048, bytes(range(32)))
+    ctxs = [bpg.Context(0) for _ in range(8)]
+    for c in ctxs:
+        c.gens_ensure(2048)
+    out, bar = {}, threading.Barrier(8)
+
+    def work(k):
+        bar.wait()
+        for rep in range(3):
+            out[(k, rep)] = gpu_prove(ctxs[k], inst, bytes(range(32)))
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for c in ctxs:
+        c.close()
+    assert len(out) == 24 and all(v == (want, Vw) for v in out.values())
