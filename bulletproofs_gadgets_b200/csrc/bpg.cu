@@ -64,6 +64,7 @@ extern "C" const char *bpg_strerror(int code) {
     }
     return "unknown";
 }
+extern "C" void bpg_set_sizing_mode(int mode);
 extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     if (!out) return BPG_E_ARG;
     *out = nullptr;
@@ -74,6 +75,8 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     if (bpg_init_constants_host() != 0) return BPG_E_ARG;
     CUDA_TRY(cudaMemcpyToSymbol(c_K, &h_K, sizeof(bpg_consts)));
     if (g_blocking_sync < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); g_blocking_sync = (e && e[0] == '1') ? 1 : 0; }
+    static bool sizing_env_read = false;
+    if (!sizing_env_read) { sizing_env_read = true; if (const char *e = getenv("BPG_SIZING_MODE")) bpg_set_sizing_mode(atoi(e)); }
     bpg_ctx *ctx = new bpg_ctx();
     ctx->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

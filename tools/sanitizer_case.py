@@ -21,9 +21,19 @@ ctx.fold_points(5, 7, G[:128], G[128:])
 ctx.mimc_hash_batch([b"abc", b"\x01" * 32])
 inst = gadgets.bounds_check_batch_instance(2, 1, seed=2)
 circ = gadgets.Circuit(ctx, inst["n"], inst["m"], inst["csr"])
-for flags in (0, 2):
+for flags in (0, 2, 16, 8):  # byte-exact, fast blinding, forced late fold, no late fold
     proof, V = circ.prove(inst, b"\x01" * 32, flags)
     assert circ.verify(inst["label"], V, proof)
+circ.close()
+# a circuit large enough for the 2^15-bucket MSM path (> 4096 terms) in both kernel sizings, with the late fold forced
+ctx.gens_ensure(4096)
+inst = circuits.chain_instance(2100, 3)
+circ = gadgets.Circuit(ctx, inst["n"], len(inst["vals"]) // 32, inst["csr"])
+for mode in (0, 1):
+    ctx.lib.bpg_set_sizing_mode(mode)
+    proof, V = circ.prove(inst, b"\x02" * 32, 16)
+    assert circ.verify(inst["label"], V, proof)
+ctx.lib.bpg_set_sizing_mode(-1)
 circ.close()
 ctx.close()
 print("sanitizer case ok")
