@@ -18,6 +18,7 @@
 #define BPG_MAX_SEGS 12
 #define BPG_CHUNK 64                  // max sorted pairs summed by one thread of the accumulate kernel (8..64, sized per MSM)
 #define BPG_SMALL_MSM_TERMS 4096      // MSMs up to this many terms use split 8-bit digits and 2 x 129 buckets per group (msm_run)
+#define BPG_PRIV_MSM_TERMS (1u << 19) // single-group MSMs from this many terms use the shared-memory privatised histogram / scatter
 #define BPG_HEAVY_SPAN 48             // buckets spanning more chunks than this go to the block-wide tree kernel
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bpg_set_cuda_error(e_, __FILE__, __LINE__); return BPG_E_CUDA; } } while (0)

@@ -152,3 +152,35 @@ def test_mimc_batch_and_trace_match_oracle(ctx):
         off += len(t)
     pre = [rnd.randbytes(rnd.randrange(1, 100)) for _ in range(200)] + [b"\x00", b"\x00" * 40, b"\xff" * 32, b"\x01" + b"\x00" * 31]
     assert ctx.mimc_hash_batch(pre) == [ol.mimc_hash(p) for p in pre]
+
+
+@pytest.mark.parametrize("dist,lg", [("uniform", 19), ("bits", 19), ("uniform", 20)])
+def test_large_msm_split_consistency(dist, lg):
+    """2^20 / 2^21-term MSM over the resident generators (shared-memory privatised histogram / scatter, >= 2^19 terms) equals the sum of
+    its four quarter ranges (2^18 terms each: plain global-atomic kernels) -- a size-independent property at BASELINE scale that
+    cross-checks the two sort paths; `bits` puts half of all pairs into bucket 1 (block-tree path for heavy buckets)."""
+    import ctypes as C
+    import numpy as np
+    import bulletproofs_gadgets_b200 as bpg
+    c = bpg.Context(0)
+    h = 1 << lg  # 2^(lg+1) terms; lg = 20: privatised histogram + plain scatter
+    c.gens_ensure(h)
+    rng = np.random.default_rng(5)
+    if dist == "uniform":
+        raw = rng.integers(0, 256, size=(2 * h, 32), dtype=np.uint8)
+        raw[:, 31] &= 0x0F
+    else:
+        raw = np.zeros((2 * h, 32), dtype=np.uint8)
+        raw[:, 0] = rng.integers(0, 2, size=2 * h, dtype=np.uint8)
+    d = c.dev_alloc(64 * h)
+    c.dev_upload(d, raw.tobytes())
+    dG, dH = d, C.c_void_p(d.value + 32 * h)
+    full = c.msm_gens_dev(dG, dH, h, 0)
+    parts = []
+    q = h // 4
+    for k in range(4):
+        parts.append(c.msm_gens_partial_dev(C.c_void_p(dG.value + 32 * q * k), C.c_void_p(dH.value + 32 * q * k), q, q * k))
+    assert c.points_sum_compress(b"".join(parts)) == full
+    assert full != bytes(32)
+    c.dev_free(d)
+    c.close()
