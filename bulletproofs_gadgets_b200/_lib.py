@@ -34,6 +34,7 @@ SYMBOLS = {
     "bpg_msm_gens_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_msm_gens_partial_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_points_sum_compress": (_i32, [_vp, _u8p, _sz, _u8p]),
+    "bpg_ctx_set_shard": (_i32, [_vp, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
     "bpg_msm_gens_partial_to_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "bpg_points_sum_compress_dev": (_i32, [_vp, _vp, _sz, _u8p]),
     "bpg_fold_points": (_i32, [_vp, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]),

@@ -345,7 +345,7 @@ static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpa
     return BPG_OK;
 }
 
-int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
+static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     uint32_t total = 0;
     for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
     plan->total = total;
@@ -410,9 +410,61 @@ int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out) {
     return BPG_OK;
 }
 
+extern "C" int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send, void *d_recv, size_t send_cap, bpg_allgather_fn allgather, void *user) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return BPG_E_ARG;
+    if (world > 1 && (!d_send || !d_recv || !allgather || send_cap < (256u << 10))) return BPG_E_ARG;
+    ctx->shard_rank = rank; ctx->shard_world = world;
+    ctx->shard_send = d_send; ctx->shard_recv = d_recv; ctx->shard_cap = send_cap;
+    ctx->shard_fn = allgather; ctx->shard_user = user;
+    return BPG_OK;
+}
+// contiguous slice [lo, hi) of n items owned by `rank` (same rule as parallel.shard_range)
+static inline void shard_slice(uint32_t n, int rank, int world, uint32_t &lo, uint32_t &hi) {
+    uint32_t base = n / (uint32_t)world, rem = n % (uint32_t)world, r = (uint32_t)rank;
+    lo = r * base + (r < rem ? r : rem);
+    hi = lo + base + (r < rem ? 1u : 0u);
+}
+// K partial points of this rank (d_pts, on stream s) -> all-gather -> d_pts[k] = sum over ranks
+static int shard_exchange_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, uint32_t K) {
+    size_t bytes = (size_t)K * sizeof(ge);
+    if (bytes > ctx->shard_cap) return BPG_E_SIZE;
+    CUDA_TRY(cudaMemcpyAsync(ctx->shard_send, d_pts, bytes, cudaMemcpyDeviceToDevice, s));
+    SYNC_TRY(ctx, s);
+    if (ctx->shard_fn(ctx->shard_user, bytes) != 0) { ctx->last_error = "all-gather callback failed"; return BPG_E_ARG; }
+    k_sum_ranks<<<LAUNCH_1D(K, 64), 0, s>>>((const ge *)ctx->shard_recv, K, (uint32_t)ctx->shard_world, d_pts);
+    KCHECK();
+    return BPG_OK;
+}
+
+int msm_run(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan_in, ge *d_out) {
+    msm_plan sliced;
+    msm_plan *plan = plan_in;
+    const bool sharded = plan_in->shard && ctx->shard_world > 1;
+    if (sharded) {
+        // every vector segment is cut by point range; single terms (blinding / Q scalars) stay with rank 0
+        sliced = *plan_in;
+        sliced.nseg = 0;
+        for (int i = 0; i < plan_in->nseg; i++) {
+            msm_seg g = plan_in->seg[i];
+            if (g.n == 1) { if (ctx->shard_rank != 0) continue; }
+            else {
+                uint32_t lo, hi;
+                shard_slice(g.n, ctx->shard_rank, ctx->shard_world, lo, hi);
+                if (hi == lo) continue;
+                g.scalars += lo; g.p0 += lo; g.j0 += lo; g.n = hi - lo;
+            }
+            sliced.seg[sliced.nseg++] = g;
+        }
+        plan = &sliced;
+    }
+    CTX_TRY(msm_run_local(ctx, s, plan, d_out));
+    if (sharded) CTX_TRY(shard_exchange_sum(ctx, s, d_out, (uint32_t)plan->ngroups));
+    return BPG_OK;
+}
+
 // Late fold (see kernels_msm.cuh): G^(k)_i, H^(k)_i for i < n' from the per-generator factors EG, EH (length N), then the
 // 16-window affine-Niels tables of those 2 n' points (+ B) in ctx->mat_tab with 2 n' + 2 points per window.
-int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean) {
+int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean, int shard) {
     uint32_t nout = 2 * nprime;
     uint32_t nb = 2 * nout * BPG_MAT_NB;
     uint32_t pt_small = nout + 2;
@@ -420,12 +472,17 @@ int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t npri
     CTX_TRY(ctx->mat_ext.ensure((size_t)BPG_NWIN * nout * sizeof(ge)));
     CTX_TRY(ctx->mat_tab.ensure((size_t)BPG_NWIN * pt_small * sizeof(ge_an)));
     uint32_t cap = (uint32_t)ctx->cap, ptotal = ctx->ptotal;
-    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)2 * N * BPG_NWIN * 2, true, ctx->tab, lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
-        if (scatter) k_mat_digits<1><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
-        else k_mat_digits<0><<<LAUNCH_1D(2 * N, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, cc, sorted);
+    const bool sharded = shard && ctx->shard_world > 1;
+    uint32_t t0 = 0, t1 = 2 * N; // this rank's slice of the 2N input terms
+    if (sharded) shard_slice(2 * N, ctx->shard_rank, ctx->shard_world, t0, t1);
+    uint32_t nt = t1 - t0;
+    CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)nt * BPG_NWIN * 2, nt != 0, ctx->tab, lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
+        if (scatter) k_mat_digits<1><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, t0, t1, cc, sorted);
+        else k_mat_digits<0><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, t0, t1, cc, sorted);
     }));
     k_mat_reduce<<<nout, 32, 0, s>>>((const ge *)ctx->buckets.p, nout, (ge *)ctx->mat_pts.p);
     KCHECK();
+    if (sharded) CTX_TRY(shard_exchange_sum(ctx, s, (ge *)ctx->mat_pts.p, nout));
     k_mat_chain<<<LAUNCH_1D(nout, 64), 0, s>>>((const ge *)ctx->mat_pts.p, nout, (ge *)ctx->mat_ext.p);
     KCHECK();
     k_mat_affine<<<LAUNCH_1D(BPG_NWIN * nout + BPG_NWIN, 64), 0, s>>>((const ge *)ctx->mat_ext.p, nout, pt_small, (ge_an *)ctx->mat_tab.p, ctx->tab, ptotal,

@@ -32,11 +32,14 @@ struct msm_seg {
     uint32_t reduce;   // 1: scalars may be >= l (host-supplied, Scalar::from_bits semantics)
     uint32_t start;    // filled by msm_run: global term index of term 0
     uint32_t alt;      // 0, or 1 + k: group ^= bit k of the term's index inside the segment (IPP rounds: left/right halves)
+    uint32_t j0;       // index of term 0 inside the caller's full vector (non-zero when a rank holds a slice of the segment)
 };
 struct msm_plan {
     msm_seg seg[BPG_MAX_SEGS]; int nseg; int ngroups; uint32_t total;
     const ge_an *tab;   // window tables the point indices refer to (nullptr: the resident generators, ctx->tab)
     uint32_t ptotal;    // points per window of `tab`
+    int shard;          // 1: with a sharded context (bpg_ctx_set_shard) every vector segment is cut by point range, this rank sums
+                        //    its slice and the partial results are all-gathered and added (protocol drivers only)
     int lean;           // 1: throughput sizing (long accumulate chunks, k_msm_rowcol_lean) -- set by the protocol drivers when
                         //    several proofs are in flight in this process (bpg_lean_now)
 };
@@ -74,6 +77,10 @@ struct bpg_ctx {
     dev_buf scratch[16];
     dev_buf batch_gh;         // batch verification: every proof's g | h scalars
     dev_buf mat_pts, mat_ext, mat_tab; // late fold: materialised G^(k) | H^(k), their window chain, their affine-Niels tables
+    // one proof split over the ranks of a node (bpg_ctx_set_shard): exchange buffers and the caller's all-gather
+    int shard_rank = 0, shard_world = 1;
+    void *shard_send = nullptr, *shard_recv = nullptr; size_t shard_cap = 0;
+    bpg_allgather_fn shard_fn = nullptr; void *shard_user = nullptr;
     void *h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<uint8_t> h_raw; // grow-only host staging of the raw transcript-RNG draws (an 8 MB malloc / free per proof
                                 // means mmap + page faults + munmap under the process-wide mm lock, 48 threads at a time)
@@ -90,4 +97,4 @@ struct bpg_ctx {
 int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s);
 int msm_run(bpg_ctx *c, cudaStream_t s, msm_plan *plan, ge *d_out /* ngroups extended points */);
 // late fold (kernels_msm.cuh): tables of the 2 n' folded generators (+ B at index 2 n') into ctx->mat_tab, ptotal = 2 n' + 2
-int msm_materialise_fold(bpg_ctx *c, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean);
+int msm_materialise_fold(bpg_ctx *c, cudaStream_t s, uint32_t N, uint32_t nprime, const sc *d_EG, const sc *d_EH, int lean, int shard);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     int d[16];
     sc_digits16(d, k);
     uint32_t grp = S.group;
-    if (S.alt) grp ^= (j >> (S.alt - 1)) & 1u;
+    if (S.alt) grp ^= ((j + S.j0) >> (S.alt - 1)) & 1u;
     uint32_t base = SPLIT ? grp * 2u * 129u : grp * BPG_NBP;
     uint32_t pidx = S.p0 + j;
 #pragma unroll
@@ -471,9 +471,9 @@ __global__ void __launch_bounds__(32) k_msm_combine(const ge *__restrict__ in8, 
 #define BPG_MAT_NB 129u
 template <int SCATTER>
 __global__ void __launch_bounds__(256) k_mat_digits(uint32_t N, uint32_t nprime, uint32_t cap, uint32_t ptotal, const sc *__restrict__ EG, const sc *__restrict__ EH,
-                                                     uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * N) return;
+                                                     uint32_t t0, uint32_t t1, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+    uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x; // [t0, t1): this rank's slice of the 2N terms (all of them unless sharded)
+    if (t >= t1) return;
     bool isH = t >= N;
     uint32_t p = isH ? t - N : t;
     sc k;
@@ -621,6 +621,16 @@ __global__ void __launch_bounds__(64) k_mat_affine(const ge *__restrict__ ext, u
         ld_an(a, &tab_main[(size_t)w * ptotal_main + pB_main]);
         st_an(&tab_small[(size_t)w * ptotal_small + npts], a);
     }
+}
+// out[k] = sum over ranks r of recv[r * K + k]   (partial results of a sharded MSM, gathered in rank order)
+__global__ void __launch_bounds__(64) k_sum_ranks(const ge *__restrict__ recv, uint32_t K, uint32_t world, ge *__restrict__ out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    ge acc, o;
+    ld_ge(acc, &recv[k]);
+#pragma unroll 1
+    for (uint32_t r = 1; r < world; r++) { ld_ge(o, &recv[(size_t)r * K + k]); ge_add_ilp(acc, acc, o); }
+    st_ge(&out[k], acc);
 }
 __global__ void __launch_bounds__(128) k_sc_fill_one(sc *__restrict__ v, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

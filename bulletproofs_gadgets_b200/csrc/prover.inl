@@ -211,6 +211,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     cudaStream_t s = ctx->stream;
     const uint32_t pB = (uint32_t)(2 * ctx->cap), pBb = pB + 1;
 
+    const int shard_on = ctx->shard_world > 1; // one proof over several ranks: MSMs cut by point range (bpg_ctx_set_shard)
     phase_trace tr;
     bpgh::Transcript t(label, label_len);
     t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
@@ -246,7 +247,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     ge *res = (ge *)ctx->results.p;
     uint8_t *d_enc = (uint8_t *)(res + 4);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
     plan.ngroups = 2;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0, uint32_t g) {
         if (!cnt) return;
@@ -285,7 +286,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
             SYNC_TRY(ctx, s); // the staging buffer is reused by this context's next proof
         }
     }
-    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
     plan.ngroups = 1;
     add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
     CTX_TRY(msm_run(ctx, s, &plan, res + 2));
@@ -382,7 +383,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     for (int j = 0; j < lgN; j++) {
         uint32_t nj = (uint32_t)(N >> j), h = nj >> 1;
         if (j == k0) {
-            CTX_TRY(msm_materialise_fold(ctx, s, (uint32_t)N, nj, d_EG, d_EH, bpg_lean_now()));
+            CTX_TRY(msm_materialise_fold(ctx, s, (uint32_t)N, nj, d_EG, d_EH, bpg_lean_now(), shard_on));
             Ncur = nj;
             tabcur = (const ge_an *)ctx->mat_tab.p; ptcur = 2 * nj + 2;
             pG = 0; pH = nj; pQ = 2 * nj;
@@ -400,7 +401,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_ipp_expand<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
         KCHECK();
-        memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
+        memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
         plan.ngroups = 2;
         plan.tab = tabcur; plan.ptotal = ptcur;
         add_seg(d_sG, Ncur, pG, 1); plan.seg[plan.nseg - 1].alt = 1 + (uint32_t)__builtin_ctz(h); // G_i: right half -> L (group 0)
@@ -645,7 +646,7 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
     CUDA_TRY(cudaEventRecord(ctx->ev2, s2));
     const uint32_t pB = (uint32_t)(2 * ctx->cap);
     msm_plan plan;
-    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now();
+    memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = 0;
     plan.ngroups = 1;
     auto add_seg = [&](const sc *sp, size_t cnt, uint32_t p0) {
         msm_seg &sg = plan.seg[plan.nseg++];

@@ -76,3 +76,36 @@ def gather_verdicts(local, n_total, device=None):
         assert len(vals) == 1, "item %d owned by %d ranks" % (k, len(vals))
         res.append(vals.pop() == 2)
     return res
+
+
+# ---------------------------------------------------------------- one proof over several ranks (BASELINE configs[3])
+_SHARD_CAP = 256 << 10  # bytes of partial points per exchange: 2 x 512 late-fold outputs x 128 B = 128 KiB at most
+
+
+def enable_sharded_prover(ctx, device):
+    """Split every large MSM of bpg_r1cs_prove on `ctx` by point range over the ranks of the default process group
+    (include/bpg.h: bpg_ctx_set_shard).  The partial points are exchanged by ONE NCCL all-gather per MSM over torch-owned
+    device buffers; every rank must then call prove() with the same arguments and gets the same proof bytes.
+    Returns a handle that must stay alive as long as the context proves (it owns the buffers and the callback)."""
+    import ctypes as C
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        ctx.check(ctx.lib.bpg_ctx_set_shard(ctx.h, 0, 1, None, None, 0, None, None))
+        return None
+    send = torch.zeros(_SHARD_CAP, dtype=torch.uint8, device=device)
+    recv = torch.zeros(_SHARD_CAP * world, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(send.device)
+
+    def _allgather(_user, nbytes):
+        try:
+            dist.all_gather_into_tensor(recv[:nbytes * world], send[:nbytes])
+            stream.synchronize()
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            return 1
+
+    cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t)(_allgather)
+    ctx.check(ctx.lib.bpg_ctx_set_shard(ctx.h, rank, world, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), _SHARD_CAP,
+                                        C.cast(cb, C.c_void_p), None))
+    return (send, recv, cb)

@@ -87,6 +87,16 @@ int bpg_msm_gens_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n,
 /* partial sum as an uncompressed extended point (128 B) for multi-GPU point-range splits, and the combiner */
 int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, uint8_t out128[128]);
 int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8_t out32[32]);
+/* ONE proof split over the ranks of a node (BASELINE configs[3]: a 2^20-multiplier circuit on 1/2/4/8 GPUs).  Every rank calls
+ * bpg_r1cs_prove with the SAME arguments; each evaluates only its point range of every large MSM (commitments, IPP rounds, the
+ * late-fold materialisation), writes its partial points (128 B each) to d_send, calls allgather(user, bytes) -- which must gather
+ * d_send[0, bytes) of all ranks into d_recv in rank order and be complete on return (NCCL all-gather on NVLink in this repo,
+ * bulletproofs_gadgets_b200/parallel.py) -- and adds the world partials.  The sums are group elements, so every rank derives
+ * the same challenges and returns the same proof bytes as an unsharded prover.  send_cap >= 256 KiB, d_recv >= world * send_cap.
+ * world = 1 switches it off. */
+typedef int (*bpg_allgather_fn)(void *user, size_t bytes_per_rank);
+int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send, void *d_recv, size_t send_cap, bpg_allgather_fn allgather, void *user);
+
 /* the same two steps with the 128-byte partial points staying on the device, for callers whose collective runs there
  * (NCCL all-gather of the partials through torch.distributed): the partial is written to d_out128 (complete when the
  * call returns), and the sum reads n gathered partials from d_ext128 (the caller orders it after its collective) */

@@ -62,3 +62,54 @@ def test_msm_point_range_split_over_two_gpus():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def _shard_worker(rank, world, port, nmul, seed, want, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import bulletproofs_gadgets_b200 as bpg
+    import bulletproofs_gadgets_b200._lib as lb
+    from bulletproofs_gadgets_b200 import parallel
+    import circuits
+    import test_gpu_r1cs as tr
+    try:
+        ctx = bpg.Context(rank)
+        ctx.gens_ensure(4096)
+        keep = parallel.enable_sharded_prover(ctx, "cuda:%d" % rank)
+        inst = circuits.chain_instance(nmul, seed)
+        ok = True
+        for flags in (lb.FLAG_FORCE_LATE_FOLD, lb.FLAG_NO_LATE_FOLD):
+            got = tr.gpu_prove(ctx, inst, bytes(range(32)), flags)
+            ok = ok and got == want
+        q.put((rank, ok))
+        del keep
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("nmul", [9, 2100])
+def test_one_proof_sharded_over_two_gpus(nmul):
+    """bpg_ctx_set_shard: every MSM of ONE proof cut by point range over 2 ranks, partial points all-gathered by NCCL.  Both ranks
+    must return exactly the oracle's proof bytes (with and without the late fold; 9 multipliers: slices of a few terms, rank 1
+    sometimes empty; 2100: the 2^15-bucket path)."""
+    import torch.multiprocessing as mp
+    import circuits
+    import test_gpu_r1cs as tr
+    inst = circuits.chain_instance(nmul, 41)
+    want = tr.oracle_prove(inst, 4096, bytes(range(32)))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, nmul, 41, want, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
