@@ -136,14 +136,20 @@ def run_reference(args):
     _emit(json.dumps(line))
 
 
-def msm_sweep(ctx, sizes, reps=5):
-    """MSM Mpoints/s over the resident generators with device-resident uniform scalars (points = n/2 G + n/2 H)"""
+def msm_sweep(ctx, sizes, reps=5, dist="uniform"):
+    """MSM Mpoints/s over the resident generators with device-resident scalars (points = n/2 G + n/2 H).
+    dist = "uniform": 252-bit scalars (SURVEY 8d MSM-uniform); "bits": scalars in {0, 1} (MSM-bits, the range-proof shape:
+    half of the pairs vanish, the other half all land in bucket 1 of window 0)"""
     import numpy as np
     out = {}
-    rng = np.random.default_rng(1)
+    rng = np.random.default_rng(1 if dist == "uniform" else 2)
     maxn = max(sizes)
-    raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
-    raw[:, 31] &= 0x0F  # < 2^252 < l : uniform reduced scalars
+    if dist == "uniform":
+        raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
+        raw[:, 31] &= 0x0F  # < 2^252 < l : uniform reduced scalars
+    else:
+        raw = np.zeros((maxn, 32), dtype=np.uint8)
+        raw[:, 0] = rng.integers(0, 2, size=maxn, dtype=np.uint8)
     d = ctx.dev_alloc(32 * maxn)
     ctx.dev_upload(d, raw.tobytes())
     import ctypes as C
@@ -158,6 +164,28 @@ def msm_sweep(ctx, sizes, reps=5):
         ms = ctx.event_elapsed_ms(0, 1) / reps
         out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3}
     ctx.dev_free(d)
+    return out
+
+
+def msm_var_sweep(ctx, sizes, reps=3):
+    """SURVEY 8d MSM-var: variable-base MSM through the host-buffer entry point bpg_msm (n compressed points + n scalars
+    uploaded, decompressed, one windowed scalar multiplication per term, tree sum): the path of the verifier's own points"""
+    import numpy as np
+    out = {}
+    rng = np.random.default_rng(3)
+    maxn = max(sizes)
+    G, H = ctx.gens_export(0, min(maxn, ctx.gens_capacity()))
+    pts = (G + H) * (1 + maxn * 32 // max(1, len(G + H)))
+    raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0F
+    sc = raw.tobytes()
+    for n in sizes:
+        ctx.msm(sc[:32 * n], pts[:32 * n])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.msm(sc[:32 * n], pts[:32 * n])
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3}
     return out
 
 
@@ -405,6 +433,8 @@ def run_ours(args):
         if not args.quick:
             ctx.gens_ensure(1 << 21)
         extras["msm"] = msm_sweep(ctx, sizes)
+        extras["msm_bits"] = msm_sweep(ctx, sizes, dist="bits")
+        extras["msm_var"] = msm_var_sweep(ctx, [1 << 10, 1 << 12] if args.quick else [1 << 10, 1 << 12, 1 << 14, 1 << 16])
 
     if world > 1 and not args.no_extras:
         extras["msm_sharded"] = msm_sharded_sweep(ctx, dist, local, rank, world, [1 << 20] if args.quick else [1 << 20, 1 << 22])

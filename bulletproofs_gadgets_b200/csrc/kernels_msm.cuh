@@ -43,29 +43,51 @@ __device__ __forceinline__ void sc_digits16(int *d, const sc &k) {
 // SPLIT = 0: bucket = group * BPG_NBP + |d|                               (2^15 buckets per group, one pair per digit)
 // SPLIT = 1: d = dl + 256 dh, buckets (2 group + 0) * 129 + |dl| and (2 group + 1) * 129 + |dh|   (small MSMs: 2 x 129 buckets
 //            per group and two pairs per digit, reduced by k_mat_reduce -- see the late-fold section below)
+// One counter update per lane, aggregated when every active lane of the warp hits the SAME counter (binary-valued witnesses
+// of range proofs: a_L in {0,1}, a_R in {0,-1} put whole warps into one bucket per window, and 2^19 same-address atomics
+// serialise; MSM-bits at 2^22 terms: 3.8 -> ms).  All 32 lanes must call it.  Returns the old counter value + the lane's
+// rank among the active lanes (its slot when scattering).
+__device__ __forceinline__ uint32_t warp_counter_add(uint32_t *__restrict__ arr, uint32_t bkt, bool active) {
+    const unsigned full = 0xFFFFFFFFu;
+    unsigned mask = __ballot_sync(full, active);
+    if (!mask) return 0;
+    int leader = __ffs(mask) - 1;
+    uint32_t lb = __shfl_sync(full, bkt, leader);
+    if (__all_sync(full, !active || bkt == lb)) {
+        uint32_t lane = threadIdx.x & 31u, base = 0;
+        if ((int)lane == leader) base = atomicAdd(&arr[lb], (uint32_t)__popc(mask));
+        base = __shfl_sync(full, base, leader);
+        return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    }
+    return active ? atomicAdd(&arr[bkt], 1u) : 0u;
+}
 template <int SCATTER, int SPLIT>
 __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.total) return;
-    int si = 0;
-#pragma unroll
-    for (int k = 1; k < BPG_MAX_SEGS; k++)
-        if (k < P.nseg && t >= P.seg[k].start) si = k;
-    const msm_seg &S = P.seg[si];
-    uint32_t j = t - S.start;
-    sc k;
-    ld_sc(k, &S.scalars[j]);
-    if (S.reduce) sc_reduce(k, k);
+    const bool valid = t < P.total; // no early return: the warp-aggregated counter update needs all 32 lanes
     int d[16];
-    sc_digits16(d, k);
-    uint32_t grp = S.group;
-    if (S.alt) grp ^= ((j + S.j0) >> (S.alt - 1)) & 1u;
+#pragma unroll
+    for (int w = 0; w < 16; w++) d[w] = 0;
+    uint32_t grp = 0, pidx = 0;
+    if (valid) {
+        int si = 0;
+#pragma unroll
+        for (int k = 1; k < BPG_MAX_SEGS; k++)
+            if (k < P.nseg && t >= P.seg[k].start) si = k;
+        const msm_seg &S = P.seg[si];
+        uint32_t j = t - S.start;
+        sc k;
+        ld_sc(k, &S.scalars[j]);
+        if (S.reduce) sc_reduce(k, k);
+        sc_digits16(d, k);
+        grp = S.group;
+        if (S.alt) grp ^= ((j + S.j0) >> (S.alt - 1)) & 1u;
+        pidx = S.p0 + j;
+    }
     uint32_t base = SPLIT ? grp * 2u * 129u : grp * BPG_NBP;
-    uint32_t pidx = S.p0 + j;
 #pragma unroll
     for (int w = 0; w < 16; w++) {
         int dw = d[w];
-        if (dw == 0) continue;
         uint32_t ent = (uint32_t)w * P.ptotal + pidx;
         if (SPLIT) {
             int dl = ((dw + 128) & 255) - 128; // [-128, 127]
@@ -73,24 +95,14 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
 #pragma unroll
             for (int part = 0; part < 2; part++) {
                 int dd = part ? dh : dl;
-                if (dd == 0) continue;
                 uint32_t mag = dd < 0 ? (uint32_t)(-dd) : (uint32_t)dd;
-                uint32_t bkt = base + part * 129u + mag;
-                if (SCATTER) {
-                    uint32_t pos = atomicAdd(&counts_or_cursor[bkt], 1u);
-                    sorted[pos] = ent | (dd < 0 ? 0x80000000u : 0u);
-                } else {
-                    atomicAdd(&counts_or_cursor[bkt], 1u);
-                }
+                uint32_t pos = warp_counter_add(counts_or_cursor, base + part * 129u + mag, dd != 0);
+                if (SCATTER && dd != 0) sorted[pos] = ent | (dd < 0 ? 0x80000000u : 0u);
             }
         } else {
             uint32_t mag = dw < 0 ? (uint32_t)(-dw) : (uint32_t)dw;
-            if (SCATTER) {
-                uint32_t pos = atomicAdd(&counts_or_cursor[base + mag], 1u);
-                sorted[pos] = ent | (dw < 0 ? 0x80000000u : 0u);
-            } else {
-                atomicAdd(&counts_or_cursor[base + mag], 1u);
-            }
+            uint32_t pos = warp_counter_add(counts_or_cursor, base + mag, dw != 0);
+            if (SCATTER && dw != 0) sorted[pos] = ent | (dw < 0 ? 0x80000000u : 0u);
         }
     }
 }
