@@ -361,7 +361,7 @@ def run_ours(args):
         raise SystemExit("concurrent contexts produced different proof bytes")
     # untimed warm-up in exactly the shape of the timed region (free-running lanes).  At least 10 steps: the 16 host threads
     # need ~1 s of load before the OS has spread them over the cores (measured: the first second runs 35 % slower)
-    warm_steps = max(args.warmup, 10)
+    warm_steps = max(args.warmup, 20)  # (10 steps = 2 s left the first timed region 10-25 % low in 2 of 8 runs)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # started before the warm-up: the first nvidia-smi invocations (cold NVML start) are slow and disturb the run

@@ -104,7 +104,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
     ctx->batch_gh.release();
-    ctx->mat_pts.release(); ctx->mat_ext.release(); ctx->mat_tab.release();
+    ctx->mat_pts.release(); ctx->mat_ext.release(); ctx->mat_tab.release(); ctx->heavy_part.release();
     DSTEP("buffers freed");
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_pairs) cudaFreeHost(ctx->prof_pairs);
@@ -339,7 +339,13 @@ static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpa
     k_msm_finish<<<LAUNCH_1D(nb, 64), 0, s>>>(offsets, nb, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
     KCHECK();
     if (any) {
-        k_msm_heavy<<<64, 64, 0, s>>>(offsets, (ge *)ctx->buckets.p, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH);
+        // heavy buckets: at most (pairs / (BPG_HEAVY_SPAN * CH)) of them can exist; segment sums, then one block per bucket
+        size_t max_heavy = maxpairs / ((size_t)BPG_HEAVY_SPAN * CH) + 1;
+        CTX_TRY(ctx->heavy_part.ensure(max_heavy * BPG_HEAVY_SEGS * sizeof(ge)));
+        unsigned hb = (unsigned)std::min<size_t>(max_heavy, 64);
+        k_msm_heavy<<<dim3(hb, BPG_HEAVY_SEGS), 64, 0, s>>>(offsets, (const ge *)ctx->partial.p, heavy, heavy + nb + 1, CH, (ge *)ctx->heavy_part.p);
+        KCHECK();
+        k_msm_heavy_final<<<hb, 32, 0, s>>>((ge *)ctx->buckets.p, heavy, heavy + nb + 1, (const ge *)ctx->heavy_part.p);
         KCHECK();
     }
     return BPG_OK;

@@ -76,6 +76,7 @@ struct bpg_ctx {
     // generic scratch
     dev_buf scratch[16];
     dev_buf batch_gh;         // batch verification: every proof's g | h scalars
+    dev_buf heavy_part;       // segment sums of heavy buckets (k_msm_heavy)
     dev_buf mat_pts, mat_ext, mat_tab; // late fold: materialised G^(k) | H^(k), their window chain, their affine-Niels tables
     // one proof split over the ranks of a node (bpg_ctx_set_shard): exchange buffers and the caller's all-gather
     int shard_rank = 0, shard_world = 1;

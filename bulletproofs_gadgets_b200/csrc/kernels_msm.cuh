@@ -325,26 +325,49 @@ __global__ void __launch_bounds__(64) k_msm_finish(const uint32_t *__restrict__ 
     }
     st_ge(&buckets[b], acc);
 }
-// one block per heavy bucket: threads stride over its partial slots, then tree-reduce in shared memory
-__global__ void __launch_bounds__(64) k_msm_heavy(const uint32_t *__restrict__ offsets, ge *__restrict__ buckets, const ge *__restrict__ partial,
-                                                   const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count, uint32_t CH) {
+// Heavy buckets (spanning more than BPG_HEAVY_SPAN chunks): grid (heavy bucket, segment).  Block (h, y) sums segment y of
+// BPG_HEAVY_SEGS equal parts of the bucket's partial slots (threads stride, then a tree in shared memory) into
+// heavy_part[h][y]; k_msm_heavy_final adds the segments.  A range-proof witness puts half of ALL pairs into one bucket
+// (2^15 partial slots at 2^22 terms): one 64-thread block per bucket took 1 ms for it.
+#define BPG_HEAVY_SEGS 32u
+__global__ void __launch_bounds__(64) k_msm_heavy(const uint32_t *__restrict__ offsets, const ge *__restrict__ partial, const uint32_t *__restrict__ heavy_list,
+                                                   const uint32_t *__restrict__ heavy_count, uint32_t CH, ge *__restrict__ heavy_part) {
     __shared__ ge smem[64];
-    uint32_t nh = *heavy_count;
+    uint32_t nh = *heavy_count, y = blockIdx.y;
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
         uint32_t s = offsets[b], e = offsets[b + 1];
         uint32_t c0 = s / CH, c1 = (e - 1) / CH;
+        uint32_t nc = c1 - c0 + 1, per = (nc + BPG_HEAVY_SEGS - 1) / BPG_HEAVY_SEGS;
+        uint32_t lo = c0 + y * per, hi = min(c1 + 1, lo + per);
         ge acc;
         ge_identity(acc);
-        for (uint32_t c = c0 + threadIdx.x; c <= c1; c += blockDim.x) {
+        for (uint32_t c = lo + threadIdx.x; c < hi; c += blockDim.x) {
             ge q;
             uint32_t slot = (c == c0 && (s % CH) != 0) ? 1u : 0u;
             ld_ge(q, &partial[2ull * c + slot]);
             ge_add_ilp(acc, acc, q);
         }
         block_tree_sum_ilp(acc, smem, 64);
-        if (threadIdx.x == 0) st_ge(&buckets[b], acc);
+        if (threadIdx.x == 0) st_ge(&heavy_part[(size_t)h * BPG_HEAVY_SEGS + y], acc);
         __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(32) k_msm_heavy_final(ge *__restrict__ buckets, const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count,
+                                                         const ge *__restrict__ heavy_part) {
+    __shared__ ge smem[32];
+    uint32_t nh = *heavy_count, lane = threadIdx.x;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        ge acc, o;
+        ld_ge(acc, &heavy_part[(size_t)h * BPG_HEAVY_SEGS + lane]);
+        st_ge(&smem[lane], acc);
+        __syncwarp();
+        for (int s2 = 16; s2 > 0; s2 >>= 1) {
+            if (lane < (uint32_t)s2) { ld_ge(o, &smem[lane + s2]); ge_add_ilp(acc, acc, o); st_ge(&smem[lane], acc); }
+            __syncwarp();
+        }
+        if (lane == 0) st_ge(&buckets[heavy_list[h]], acc);
+        __syncwarp();
     }
 }
 
