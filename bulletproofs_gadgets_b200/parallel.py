@@ -79,7 +79,7 @@ def gather_verdicts(local, n_total, device=None):
 
 
 # ---------------------------------------------------------------- one proof over several ranks (BASELINE configs[3])
-_SHARD_CAP = 256 << 10  # bytes of partial points per exchange: 2 x 512 late-fold outputs x 128 B = 128 KiB at most
+_SHARD_CAP = 2 << 20  # bytes of partial points per exchange: the late fold sends 2 x (N / 256) outputs x 128 B = 1 MiB at N = 2^20
 
 
 def enable_sharded_prover(ctx, device):

@@ -92,7 +92,8 @@ int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8
  * late-fold materialisation), writes its partial points (128 B each) to d_send, calls allgather(user, bytes) -- which must gather
  * d_send[0, bytes) of all ranks into d_recv in rank order and be complete on return (NCCL all-gather on NVLink in this repo,
  * bulletproofs_gadgets_b200/parallel.py) -- and adds the world partials.  The sums are group elements, so every rank derives
- * the same challenges and returns the same proof bytes as an unsharded prover.  send_cap >= 256 KiB, d_recv >= world * send_cap.
+ * the same challenges and returns the same proof bytes as an unsharded prover.  send_cap >= 256 KiB (2 MiB lets the late fold
+ * keep N / 256 generators at N = 2^20), d_recv >= world * send_cap.
  * world = 1 switches it off. */
 typedef int (*bpg_allgather_fn)(void *user, size_t bytes_per_rank);
 int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send, void *d_recv, size_t send_cap, bpg_allgather_fn allgather, void *user);
