@@ -387,8 +387,11 @@ def run_ours(args):
     # the same kernel timed alone (one prover, nothing else on the GPU): this is the figure the roofline fraction is quoted on
     barrier_max(dist, local, 0.0)
     ctx.prof_enable(True)
+    ctx.event_record(4)
     for _ in range(3):
-        lanes[0].prove(ext, RES, True)
+        lanes[0].prove(ext, RES | bpg._lib.FLAG_FAST_BLINDING, True)  # device-side blinding: no 45 ms host RNG gap inside the events
+    ctx.event_record(5)
+    solo_ms = ctx.event_elapsed_ms(4, 5)
     # A proof launches the kernel at two very different sizes: the full-size MSMs over the resident generators (commitments,
     # first IPP rounds, the late-fold materialisation: >= 1 M pairs each, > 95 % of the kernel's time) and the tiny ones over
     # the 2 x 512 materialised generators (late IPP rounds, ~16 K pairs, launch-latency bound).  The roofline is quoted on the
@@ -490,6 +493,8 @@ def run_ours(args):
                              "avg_launch_ms": kms / nl if nl else None, "pairs_per_launch": pairs / nl if nl else None,
                              "note": "CUDA events around every full-size launch (>= 25 % of the largest pair count) of 3 proofs run alone after the timed region (kernel timed alone)",
                              "small_launches": small_launches,
+                             "share_of_step": (sum(m for m, _ in per_launch) / solo_ms) if solo_ms > 0 else None,
+                             "share_note": "all k_msm_accumulate launches / device time of the same 3 solo proofs (compare profiles/r01_launch_summary_final.txt)",
                              "in_timed_region": {"launches": int(nl_c), "avg_launch_ms": kms_c / nl_c if nl_c else None,
                                                  "note": "lane 0's launches while %d other provers share the GPU" % (K - 1)},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
