@@ -13,6 +13,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <thread>
 
 static thread_local std::string g_cuda_err;
@@ -150,7 +152,6 @@ gens_tables::~gens_tables() {
     if (tab) cudaFree(tab);
     if (comb) cudaFree(comb);
 }
-#include <mutex>
 static std::mutex g_gens_mu;
 static std::weak_ptr<gens_tables> g_gens[64]; // per device: the largest table set currently alive
 
@@ -279,7 +280,6 @@ static int run_points_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, size_t n, ge 
 // Protocol calls in flight in this process.  With several provers / verifiers sharing the GPU the kernels are sized for
 // work efficiency (long accumulate chunks: fewer bucket runs cut at chunk borders, measured +5 % proofs/s at half a wave;
 // work-lean row/column reduction); a lone caller gets the latency-oriented sizes (two waves, shallow reductions).
-#include <atomic>
 static std::atomic<int> g_inflight{0};
 struct bpg_inflight_guard {
     bpg_inflight_guard() { g_inflight.fetch_add(1, std::memory_order_relaxed); }
