@@ -369,7 +369,10 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
             if (scatter) k_msm_digits<1, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
             else k_msm_digits<0, 1><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
         }));
-        k_small_reduce<<<G, 256, 0, s>>>((const ge *)ctx->buckets.p, d_out);
+        CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
+        k_small_reduce<<<2 * G, 128, 0, s>>>((const ge *)ctx->buckets.p, (ge *)ctx->lvlQ.p);
+        KCHECK();
+        k_small_combine<<<1, 32, 0, s>>>((const ge *)ctx->lvlQ.p, (uint32_t)G, d_out);
         KCHECK();
         return BPG_OK;
     }

@@ -586,16 +586,17 @@ __global__ void __launch_bounds__(32) k_mat_reduce(const ge *__restrict__ bucket
     }
 }
 // Latency-lean reduction of the same 2 x 129 bucket layout for the few groups of a SMALL MSM (late IPP rounds: 2 groups,
-// nothing else of this proof can run until L_j, R_j are known).  One 256-thread block per group, thread = (set, b - 1):
-// b * T_b by a fixed 8-step double-and-add (uniform across the warp), block-wide tree, then low + 2^8 high.
+// nothing else of this proof can run until L_j, R_j are known).  One 128-thread block per (group, set), thread = b - 1:
+// b * T_b by a fixed 8-step double-and-add (uniform across the warp), block-wide tree; k_small_combine: low + 2^8 high.
 // Depth ~ 16 + 8 + 9 point operations instead of ~ 55 in k_mat_reduce, at ~ 3x its work (irrelevant for 2 groups; the
 // late-fold materialisation with its 1024 outputs keeps the work-lean kernel).
-__global__ void __launch_bounds__(256) k_small_reduce(const ge *__restrict__ buckets, ge *__restrict__ out) {
-    __shared__ ge smem[256];
-    uint32_t g = blockIdx.x, t = threadIdx.x;
-    uint32_t set = t >> 7, b = (t & 127u) + 1u;
+__global__ void __launch_bounds__(128) k_small_reduce(const ge *__restrict__ buckets, ge *__restrict__ part) {
+    // grid = 2 * groups blocks of 128 threads: block (2 g + set) weights and sums the 128 buckets of one set.  One warp per
+    // SM sub-partition: with both sets in one 256-thread block two warps shared each integer pipe and every step took 1.4 x longer.
+    __shared__ ge smem[128];
+    uint32_t gs = blockIdx.x, t = threadIdx.x, b = t + 1u;
     ge p, acc;
-    ld_ge(p, &buckets[((size_t)2 * g + set) * BPG_MAT_NB + b]);
+    ld_ge(p, &buckets[(size_t)gs * BPG_MAT_NB + b]);
     ge_identity(acc);
 #pragma unroll 1
     for (int k = 7; k >= 0; k--) {
@@ -604,8 +605,8 @@ __global__ void __launch_bounds__(256) k_small_reduce(const ge *__restrict__ buc
     }
     st_ge(&smem[t], acc);
     __syncthreads();
-    for (int s2 = 64; s2 > 0; s2 >>= 1) { // two independent trees: threads [0,128) and [128,256)
-        if ((t & 127u) < (uint32_t)s2) {
+    for (int s2 = 64; s2 > 0; s2 >>= 1) {
+        if (t < (uint32_t)s2) {
             ge o;
             ld_ge(o, &smem[t + s2]);
             ge_add_ilp(acc, acc, o);
@@ -613,14 +614,18 @@ __global__ void __launch_bounds__(256) k_small_reduce(const ge *__restrict__ buc
         }
         __syncthreads();
     }
-    if (t == 0) {
-        ge hi;
-        ld_ge(hi, &smem[128]);
+    if (t == 0) st_ge(&part[gs], acc);
+}
+// out[g] = part[2 g] + 2^8 part[2 g + 1]
+__global__ void __launch_bounds__(32) k_small_combine(const ge *__restrict__ part, uint32_t G, ge *__restrict__ out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    ge lo, hi;
+    ld_ge(lo, &part[2 * g]); ld_ge(hi, &part[2 * g + 1]);
 #pragma unroll 1
-        for (int k = 0; k < 8; k++) ge_dbl_ilp(hi, hi);
-        ge_add_ilp(acc, acc, hi);
-        st_ge(&out[g], acc);
-    }
+    for (int k = 0; k < 8; k++) ge_dbl_ilp(hi, hi);
+    ge_add_ilp(lo, lo, hi);
+    st_ge(&out[g], lo);
 }
 // window chain of the materialised points: ext[w][q] = 2^(16 w) P_q  (one thread per point, 240 doublings)
 __global__ void __launch_bounds__(64) k_mat_chain(const ge *__restrict__ pts, uint32_t npts, ge *__restrict__ ext) {
