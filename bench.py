@@ -294,8 +294,10 @@ def run_ours(args):
         # The provers' bulk transcript-RNG draws are batched into SIMD lanes by the library (host_rng_service.h) and the waiting
         # threads sleep, so the prover count is set by latency hiding, not by the core count: a proof spends ~60-100 ms in the
         # shared RNG lanes and ~12 ms on the device, and ~300 proofs/s need ~30+ proofs in flight.
-        # Measured on one B200 + 16 cores: K = 24 / 48 / 64 -> 249 / 272 / 297 proofs/s byte-exact (fast blinding: 315).
-        K = 64
+        # Measured on one B200 + 16 cores: K = 24 / 48 / 64 / 96 / 128 -> 249 / 272 / 312 / 328 / 329 proofs/s byte-exact
+        # (fast blinding: 327-332, i.e. 96 provers close the gap).  With fewer than 8 cores per GPU the host is the limit and
+        # more threads do not help (8 GPUs on 32 cores were measured with 64).
+        K = 96 if per_gpu >= 8 else 64
     # more prover threads than cores: they sleep while they wait for the device (bpg_set_blocking_sync); the solo latency
     # measurements further down (single proof, MSM sweeps) switch back to spinning
     blocking = K * world > cores
