@@ -6,11 +6,13 @@
 
 Metric (BASELINE.json): R1CS proofs/sec (and MSM Mpoints/sec in the `msm` sweep) on BASELINE configs[1]:
 "merkle_tree membership with mimc_hash, depth 32, single proof" (n = 63 180 multipliers, N = 2^16, m = 4).
-A proof = Pedersen commits, 3 commitment MSMs, polynomial phase, 16 IPP rounds of that circuit.  A step = one proof
-on each of K concurrent provers per GPU (independent host thread + bpg_ctx each; K is reported in `config`); the provers
-free-run through their `steps` proofs inside the timed region, which hides the sequential host-side Merlin RNG of one
-proof behind the device work of the others; `single_proof_latency_ms` is the
-un-overlapped figure.  Every rank runs its own provers (weak scaling, no data-path collective).
+A proof = Pedersen commits, 3 commitment MSMs, polynomial phase, 16 IPP rounds of that circuit.  A step = K proofs, one
+per concurrent prover of the GPU (independent host thread + bpg_ctx each; K is reported in `config`); the K * steps
+proofs of the timed region are handed out to the free-running provers one at a time, which hides the sequential host-side
+Merlin RNG of one proof (its stream shares SIMD lanes with the other provers' streams) behind the device work of the
+others; `single_proof_latency_ms` is the un-overlapped figure.  Every rank runs its own provers (weak scaling, no data-path
+collective).  Extras for N > 1: `msm_sharded` (one MSM split by point range) and `one_proof_2p20` (ONE large proof split
+over the ranks, BASELINE configs[3]).
 
   value  proofs/s with the witness vectors already resident in HBM (BPG_FLAG_WITNESS_ON_DEVICE)
   e2e    proofs/s through the C ABI with HOST buffers: witness H2D, proof + commitments D2H inside the timed region
