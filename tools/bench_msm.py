@@ -1,4 +1,4 @@
-"""MSM sweep + accumulate-kernel timing for one library build / BPG_ACC_VARIANT (development aid).
+"""MSM sweep + accumulate-kernel timing for one library build (development aid; LABEL=... tags the output line).
 usage: python tools/bench_msm.py [log2 sizes...]  -> one JSON line"""
 import json
 import os
@@ -11,7 +11,7 @@ import bulletproofs_gadgets_b200 as bpg  # noqa: E402
 sizes = [1 << int(a) for a in sys.argv[1:]] or [1 << 17, 1 << 20]
 ctx = bpg.Context(0)
 ctx.gens_ensure(max(sizes) // 2)
-out = {"variant": os.environ.get("BPG_ACC_VARIANT", "0")}
+out = {"variant": os.environ.get("LABEL", os.environ.get("BPG_ACC_VARIANT", "0"))}
 for n in sizes:
     ctx.prof_enable(True)
     r = bench.msm_sweep(ctx, [n], reps=8)
