@@ -456,6 +456,11 @@ def run_ours(args):
         cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": cores, "kind": "port",
                "sample": "1 complete proof of the same depth-32 circuit on all host cores (oracle/bpo.c, OpenMP)",
                "proof_bytes_equal_gpu": proof_cpu == proof_same}
+        if not args.quick:
+            # what the reference binary does today: one thread (SURVEY 8d asks for both figures)
+            t_one, proof_one = oracle_prove_time(dict(inst), 1)
+            cpu["single_thread_value"] = 1.0 / t_one
+            cpu["single_thread_bytes_equal"] = proof_one == proof_cpu
 
     if rank == 0:
         peaks = {}
