@@ -53,3 +53,30 @@ def test_concurrent_streams_of_different_lengths():
         t.join()
     for i in range(13):
         assert res[i] == _draw(lib, b"L%d" % i, ext, 1, 700 + 977 * i, 0), i
+
+
+def test_stress_random_arrivals():
+    """32 streams arriving at random times with lengths from 1 to 20 000 draws, three waves: leaders take over from each other
+    (hand-back of unfinished streams), late streams are adopted into free lanes, extra leaders appear when all lanes are busy"""
+    import random
+    import time
+    lib = _lib.load()
+    ext = bytes(range(64, 96))
+    rnd = random.Random(99)
+    for wave in range(3):
+        jobs = [(b"S%d-%d" % (wave, i), rnd.choice([1, 7, 300, 513, 4000, 20000]), rnd.random() * 0.02) for i in range(32)]
+        res = {}
+
+        def work(k):
+            label, count, delay = jobs[k]
+            time.sleep(delay)
+            res[k] = _draw(lib, label, ext, 1, count, 1)
+
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=120)
+            assert not t.is_alive(), "a stream was never served"
+        for k, (label, count, _) in enumerate(jobs):
+            assert res[k] == _draw(lib, label, ext, 1, count, 0), (wave, k)
