@@ -17,6 +17,8 @@
 #include <mutex>
 #include <thread>
 
+#include <strings.h>
+
 static thread_local std::string g_cuda_err;
 void bpg_set_cuda_error(cudaError_t e, const char *file, int line) {
     char buf[512];
@@ -38,20 +40,25 @@ void dev_buf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
 // Wait for the context's stream.  With BPG_BLOCKING_SYNC=1 the host thread sleeps on an event created with
 // cudaEventBlockingSync instead of spinning, which leaves the core to the other provers' transcript RNG.
-static int g_blocking_sync = -1;
+// (process-wide switches are atomics: prover threads read them while another thread may call the setter)
+static std::atomic<int> g_blocking_sync{-1};
+static inline int blocking_sync_now() {
+    int v = g_blocking_sync.load(std::memory_order_relaxed);
+    if (v < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); v = (e && e[0] == '1') ? 1 : 0; int exp = -1; g_blocking_sync.compare_exchange_strong(exp, v); v = g_blocking_sync.load(); }
+    return v;
+}
 int bpg_stream_sync(bpg_ctx *ctx, cudaStream_t s) {
-    if (g_blocking_sync < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); g_blocking_sync = (e && e[0] == '1') ? 1 : 0; }
-    if (!g_blocking_sync || s != ctx->stream) { CUDA_TRY(cudaStreamSynchronize(s)); return BPG_OK; }
+    if (!blocking_sync_now() || s != ctx->stream) { CUDA_TRY(cudaStreamSynchronize(s)); return BPG_OK; }
     CUDA_TRY(cudaEventRecord(ctx->ev, s));
     CUDA_TRY(cudaEventSynchronize(ctx->ev));
     return BPG_OK;
 }
-extern "C" void bpg_set_blocking_sync(int on) { g_blocking_sync = on ? 1 : 0; }
+extern "C" void bpg_set_blocking_sync(int on) { g_blocking_sync.store(on ? 1 : 0); }
 #define SYNC_TRY(ctx, s) CTX_TRY(bpg_stream_sync(ctx, s))
 // Device -> pageable host copies return only when the copy is done, and the driver SPINS for everything queued before
 // them (measured: 47 ms of host CPU per proof with 48 provers sharing a GPU, starving the transcript-RNG lanes).  In
 // blocking-sync mode the thread first sleeps on the stream's event, so the copy finds an idle stream.
-#define D2H_TRY(ctx, dst, src, bytes, s) do { if (g_blocking_sync == 1) SYNC_TRY(ctx, s); CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); } while (0)
+#define D2H_TRY(ctx, dst, src, bytes, s) do { if (blocking_sync_now() == 1) SYNC_TRY(ctx, s); CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); } while (0)
 
 // ================================================================ context
 extern "C" const char *bpg_strerror(int code) {
@@ -67,6 +74,21 @@ extern "C" const char *bpg_strerror(int code) {
     return "unknown";
 }
 extern "C" void bpg_set_sizing_mode(int mode);
+extern "C" void bpg_ctx_destroy(bpg_ctx *ctx);
+// __constant__ symbols are per-device globals: uploaded once per device, under a lock, and complete (device-wide sync) before
+// any kernel of any context can run -- the contexts' streams are cudaStreamNonBlocking and do not order against the legacy
+// default stream the symbol copy uses.
+static std::mutex g_const_mu;
+static bool g_const_done[64] = {false};
+static int upload_device_constants(int device) {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    if (device < 64 && g_const_done[device]) return BPG_OK;
+    if (bpg_init_constants_host() != 0) return BPG_E_ARG;
+    CUDA_TRY(cudaMemcpyToSymbol(c_K, &h_K, sizeof(bpg_consts)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (device < 64) g_const_done[device] = true;
+    return BPG_OK;
+}
 extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     if (!out) return BPG_E_ARG;
     *out = nullptr;
@@ -74,17 +96,22 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(device));
-    if (bpg_init_constants_host() != 0) return BPG_E_ARG;
-    CUDA_TRY(cudaMemcpyToSymbol(c_K, &h_K, sizeof(bpg_consts)));
-    if (g_blocking_sync < 0) { const char *e = getenv("BPG_BLOCKING_SYNC"); g_blocking_sync = (e && e[0] == '1') ? 1 : 0; }
-    static bool sizing_env_read = false;
-    if (!sizing_env_read) { sizing_env_read = true; if (const char *e = getenv("BPG_SIZING_MODE")) bpg_set_sizing_mode(atoi(e)); }
+    int rc = upload_device_constants(device);
+    if (rc != BPG_OK) return rc;
+    (void)blocking_sync_now();
+    static std::once_flag sizing_once;
+    std::call_once(sizing_once, [] { if (const char *e = getenv("BPG_SIZING_MODE")) bpg_set_sizing_mode(atoi(e)); });
     bpg_ctx *ctx = new bpg_ctx();
     ctx->device = device;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming));
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming);
+    if (e != cudaSuccess) { // nothing of a half-built context may leak
+        bpg_set_cuda_error(e, __FILE__, __LINE__);
+        bpg_ctx_destroy(ctx);
+        return BPG_E_CUDA;
+    }
     *out = ctx;
     return BPG_OK;
 }
@@ -99,6 +126,9 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     ctx->prof_ev.clear();
     DSTEP("prof events destroyed");
+    // prover secrets (witness, blindings, transcript-RNG draws) do not outlive the context
+    for (int i : {8, 9, 12, 13}) if (ctx->scratch[i].p) cudaMemset(ctx->scratch[i].p, 0, ctx->scratch[i].cap);
+    if (!ctx->h_raw.empty()) explicit_bzero(ctx->h_raw.data(), ctx->h_raw.size());
     ctx->gens.reset(); // the tables are freed with their last user
     ctx->tab = nullptr; ctx->comb = nullptr;
     DSTEP("tables freed");
@@ -383,12 +413,9 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
     bool priv = (G == 1 && total >= BPG_PRIV_MSM_TERMS);
     int sms = 0;
     if (priv) {
-        static int attr_set = 0;
-        if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_msm_hist_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPG_NBP * 4)));
-            CUDA_TRY(cudaFuncSetAttribute(k_msm_scatter_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPG_NBP * 4)));
-            attr_set = 1;
-        }
+        // (idempotent and cheap; setting it per call keeps it correct for every device without shared mutable state)
+        CUDA_TRY(cudaFuncSetAttribute(k_msm_hist_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPG_NBP * 4)));
+        CUDA_TRY(cudaFuncSetAttribute(k_msm_scatter_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPG_NBP * 4)));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     }
     CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)total * BPG_NWIN, total != 0, tab, plan->lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {

@@ -10,6 +10,7 @@
 // unfinished ones back and another waiter takes over.  The bytes are those of host_merlin.h's scalar TranscriptRng.
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -101,6 +102,7 @@ class RngService {
                 break;
             }
         }
+        explicit_bzero(soa, sizeof soa);
         leaders--;
         cv.notify_all();
     }
@@ -128,6 +130,7 @@ public:
             waits++;
         }
         memcpy(s.st, job.st, sizeof job.st); // position and flags are those of the steady state again
+        explicit_bzero(job.st, sizeof job.st); // the stream state is a prover secret
     }
 };
 

@@ -11,7 +11,12 @@ extern "C" int bpg_mimc_set_constants(bpg_ctx *ctx, const uint8_t *consts486x32)
         t.v[7] &= 0x7FFFFFFFu; // Scalar::from_bits (mimc.rs:69)
         sc_reduce(c[i], t);
     }
-    CUDA_TRY(cudaMemcpyToSymbol(c_mimc, c.data(), sizeof(sc) * MIMC_ROUNDS));
+    {   // per-device symbol: uploaded under the constants lock and complete before any kernel can read it
+        std::lock_guard<std::mutex> lk(g_const_mu);
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpyToSymbol(c_mimc, c.data(), sizeof(sc) * MIMC_ROUNDS));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     return BPG_OK;
 }
 extern "C" int bpg_mimc_sponge_batch(bpg_ctx *ctx, const uint8_t *blocks, const uint32_t *block_off, size_t n, uint8_t *out32, uint8_t *trace) {
@@ -284,6 +289,7 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
             k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)ctx->scratch[12].p, (uint32_t)n, d_sL, d_sR);
             KCHECK();
             SYNC_TRY(ctx, s); // the staging buffer is reused by this context's next proof
+            explicit_bzero(raw.data(), 128 * n); // the raw draws are prover secrets (they determine s_L, s_R)
         }
     }
     memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
@@ -439,6 +445,14 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     sc_tobytes(o, tx); sc_tobytes(o + 32, txb); sc_tobytes(o + 64, eb); o += 96;
     memcpy(o, LR.data(), 64 * (size_t)lgN); o += 64 * (size_t)lgN;
     sc_tobytes(o, fab[0]); sc_tobytes(o + 32, fab[1]); o += 64;
+    // Prover secrets do not outlive the call: witness, s_L / s_R, l(x) / r(x) vectors, blinding scalars and seeds on the device
+    // (asynchronous, ordered before this context's next use of the buffers), blindings and the RNG state on the host.
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch[8].p, 0, (5 * N + 8) * sizeof(sc), s));
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch[12].p, 0, (4 * N + 8) * sizeof(sc), s));
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch[13].p, 0, (4 * N + 8) * sizeof(sc), s));
+    CUDA_TRY(cudaMemsetAsync(d_small, 0, 256 * sizeof(sc), s));
+    explicit_bzero(&rng, sizeof rng); explicit_bzero(tb, sizeof tb); explicit_bzero(h_small, sizeof h_small);
+    explicit_bzero(&ib, sizeof ib); explicit_bzero(&ob, sizeof ob); explicit_bzero(&sb, sizeof sb);
     return (long)(o - proof);
 }
 
@@ -678,7 +692,8 @@ extern "C" int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     bpg_inflight_guard inflight_;
     if (!accept) return BPG_E_ARG;
     *accept = 0;
-    if (c && c->m && !V32) return BPG_E_ARG;
+    if (!ctx || !c || !label || !proof || !ext_rng32) return BPG_E_ARG;
+    if (c->m && !V32) return BPG_E_ARG;
     vprep p;
     CUDA_TRY(cudaSetDevice(ctx->device));
     CTX_TRY(ctx->scratch[7].ensure((c->m + 4) * sizeof(sc)));
@@ -756,19 +771,30 @@ extern "C" int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *co
     D2H_TRY(ctx, h_slots.data(), d_slots, 32 * slots, ctx->stream);
     SYNC_TRY(ctx, ctx->stream);
     for (size_t i : idx) verify_complete(preps[i], h_slots.data() + soff[i]);
-    // weights: rho_i = wide_reduce(SHAKE256("bpg batch" || all ext_rng32 || i))  -- unpredictable to the provers
+    // Weights rho_i = wide_reduce(64-byte block i of SHAKE256("bpg batch v2" || count || for every proof: label, V, proof bytes
+    // (length-prefixed) || all ext_rng32)).  They are bound to the STATEMENTS and PROOFS of the batch, not only to the caller's
+    // randomness: the final IPP scalars a, b of a proof are in no transcript, so weights that ignore the proof bytes would let a
+    // prover who can predict ext_rng32 submit two tampered copies whose errors cancel (rho_1 d_1 + rho_2 d_2 = 0).  With the
+    // proofs absorbed the weights are a random-oracle output the prover cannot choose its proofs against; ext_rng32 (fresh
+    // secret randomness, the reference's thread_rng) additionally hides them from an offline search.
     std::vector<sc> rhos(count);
-    for (size_t i : idx) {
+    {
         bpgh::Sponge sp(136);
-        sp.absorb((const uint8_t *)"bpg batch", 9);
+        auto absorb_u64 = [&](uint64_t v) { uint8_t b8[8]; for (int b = 0; b < 8; b++) b8[b] = (uint8_t)(v >> (8 * b)); sp.absorb(b8, 8); };
+        sp.absorb((const uint8_t *)"bpg batch v2", 12);
+        absorb_u64(count);
+        for (size_t i = 0; i < count; i++) {
+            absorb_u64(label_lens[i]); sp.absorb(labels[i], label_lens[i]);
+            absorb_u64(circuits[i]->m); if (circuits[i]->m) sp.absorb(V32[i], 32 * circuits[i]->m);
+            absorb_u64(proof_lens[i]); sp.absorb(proofs[i], proof_lens[i]);
+        }
         sp.absorb(ext_rng32, 32 * count);
-        uint8_t ib[8];
-        for (int b = 0; b < 8; b++) ib[b] = (uint8_t)((uint64_t)i >> (8 * b));
-        sp.absorb(ib, 8);
         sp.finish(0x1F);
-        uint8_t w[64];
-        sp.squeeze(w, 64);
-        rhos[i] = h_wide(w);
+        for (size_t i = 0; i < count; i++) {
+            uint8_t w[64];
+            sp.squeeze(w, 64);
+            rhos[i] = h_wide(w);
+        }
     }
     return verify_bisect(ctx, preps, rhos, idx, 0, idx.size(), false, accept);
 }

@@ -14,6 +14,7 @@ Scalar semantics follow SURVEY App. C: witness / instance values enter through S
 """
 import os
 import random
+import secrets
 import re
 
 from .api import L_ORDER, ONE, Prover, Verifier, BulletproofGens, R1CSError
@@ -372,9 +373,13 @@ class Assignments:
 
 # ----------------------------------------------------------------------------- prover driver
 class ProverRun:
-    def __init__(self, label, gadgets_text, inst_text, wtns_text, seed=0, ctx=None):
+    def __init__(self, label, gadgets_text, inst_text, wtns_text, test_seed=None, ctx=None):
+        """Every Pedersen blinding is an independent draw from the OS CSPRNG, as the reference's
+        Scalar::random(&mut thread_rng()) (commitments.rs:27,39  gadget.rs:31).  `test_seed` (tests / benchmarks ONLY)
+        replaces it with a seeded, reproducible stream so proof bytes can be compared with the oracle: such
+        commitments are NOT hiding."""
         self.prover = Prover.new(label, ctx=ctx)
-        self.rng = random.Random(seed)
+        self._test_rng = random.Random(test_seed) if test_seed is not None else None
         self.a = Assignments()
         self.coms_names = []  # name of every committed variable, in commit order
         self.counter = _Counter()
@@ -397,7 +402,8 @@ class ProverRun:
         assign_buffer(self.prover, top)
 
     def _commit(self, scalar, name):
-        _, var = self.prover.commit(scalar, self.rng.randrange(L))
+        blinding = self._test_rng.randrange(L) if self._test_rng is not None else secrets.randbelow(L)
+        _, var = self.prover.commit(scalar, blinding)
         self.coms_names.append(name)
         return var
 
@@ -705,11 +711,11 @@ def _read(path):
         return f.read()
 
 
-def prover_main(stem, seed=None, ext_rng32=None, ctx=None, label=None):
-    """`prover <stem>`: reads <stem>.gadgets/.inst/.wtns, writes <stem>.coms and <stem>.proof; returns #constraints"""
-    seed = random.SystemRandom().getrandbits(64) if seed is None else seed
+def prover_main(stem, test_seed=None, ext_rng32=None, ctx=None, label=None):
+    """`prover <stem>`: reads <stem>.gadgets/.inst/.wtns, writes <stem>.coms and <stem>.proof; returns #constraints.
+    Blindings come from the OS CSPRNG unless `test_seed` is given (tests only, see ProverRun)."""
     run = ProverRun((label or stem).encode() if isinstance(label or stem, str) else (label or stem), _read(stem + ".gadgets"), _read(stem + ".inst"),
-                    _read(stem + ".wtns"), seed=seed, ctx=ctx)
+                    _read(stem + ".wtns"), test_seed=test_seed, ctx=ctx)
     coms, proof, nc = run.finish(ext_rng32=ext_rng32)
     with open(stem + ".coms", "w") as f:
         f.write(coms)

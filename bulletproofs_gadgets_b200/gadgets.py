@@ -355,8 +355,11 @@ class Circuit:
             self.ctx.check(rc)
         return proof.raw[:rc], V.raw[:32 * self.m]
 
-    def verify(self, label, V, proof, ext_rng32=bytes(32), flags=0):
+    def verify(self, label, V, proof, ext_rng32=None, flags=0):
+        """ext_rng32 stands for the verifier's thread_rng draw: fresh secret randomness unless a test pins it"""
         import ctypes as C
+        if ext_rng32 is None:
+            ext_rng32 = os.urandom(32)
         acc = C.c_int(0)
         self.ctx.check(self.ctx.lib.bpg_r1cs_verify(self.ctx.h, self.h, label, len(label), V, proof, len(proof), ext_rng32, flags, C.byref(acc)))
         return bool(acc.value)

@@ -144,7 +144,10 @@ int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t l
 /* Batch verification: accept[i] = what bpg_r1cs_verify returns for proof i.  The proofs are combined
  * with random weights into ONE fixed-base multiscalar multiplication over the resident generators plus one
  * variable-base launch over all proofs' own points; a failing combination is bisected until the invalid proofs are
- * isolated, so verdicts equal one-by-one verification.  ext_rng32 = count x 32 bytes (one thread_rng stand-in per proof). */
+ * isolated, so verdicts equal one-by-one verification.  ext_rng32 = count x 32 bytes (one thread_rng stand-in per proof):
+ * it MUST be fresh secret randomness (the reference draws it from thread_rng inside Verifier::verify).  The combination
+ * weights are derived from every proof's label, commitments and full proof bytes together with ext_rng32, so they are
+ * bound to the statements being checked and cannot be anticipated by the provers. */
 int bpg_r1cs_verify_batch(bpg_ctx *ctx, size_t count, bpg_circuit *const *circuits, const uint8_t *const *labels,
                           const size_t *label_lens, const uint8_t *const *V32, const uint8_t *const *proofs,
                           const size_t *proof_lens, const uint8_t *ext_rng32, unsigned flags, int *accept);

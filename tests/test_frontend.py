@@ -42,7 +42,7 @@ def unsatisfied_rows(p):
 @pytest.mark.parametrize("name", sorted(SIZES))
 def test_fixture_assembles_like_the_reference(name):
     from bulletproofs_gadgets_b200 import frontend as fe
-    run = fe.ProverRun(name.encode(), rd(name + ".gadgets"), rd(name + ".inst"), rd(name + ".wtns"), seed=1)
+    run = fe.ProverRun(name.encode(), rd(name + ".gadgets"), rd(name + ".inst"), rd(name + ".wtns"), test_seed=1)
     p = run.prover
     n, m = SIZES[name]
     assert p.get_num_multiplications() == n
@@ -67,13 +67,13 @@ def test_falsified_statements_leave_constraints_unsatisfied():
              ("HASH W1 W0\n", "", "W0 = 0x43\nW1 = 0x0cfb0c17618211c607febf703ac3f3078f7d96798fae9d4a1682bc592f7cb127\n"),
              ("OR\n[\n{\nEQUALS W0 W1\n}\n{\nLESS_THAN W1 W0\n}\n]\n", "", "W0 = 0x43\nW1 = 0x44\n")]
     for gadgets, inst, wtns in cases:
-        run = fe.ProverRun(b"neg", gadgets, inst, wtns, seed=2)
+        run = fe.ProverRun(b"neg", gadgets, inst, wtns, test_seed=2)
         assert unsatisfied_rows(run.prover) > 0, gadgets
     # ... and the true versions are satisfied (incl. an OR whose first clause is false)
     for gadgets, inst, wtns in [("OR\n[\n{\nEQUALS W0 W1\n}\n{\nLESS_THAN W0 W1\n}\n]\n", "", "W0 = 0x43\nW1 = 0x44\n"),
                                 ("HASH W1 W0\n", "", "W0 = 0x43\nW1 = 0x0cfb0c17618211c607febf703ac3f3078f7d96798fae9d4a1682bc592f7cb126\n"),
                                 ("SET_MEMBER W0 I0 I1\n", "I0 = 0x11\nI1 = 0x64\n", "W0 = 0x64\n")]:
-        run = fe.ProverRun(b"pos", gadgets, inst, wtns, seed=2)
+        run = fe.ProverRun(b"pos", gadgets, inst, wtns, test_seed=2)
         assert unsatisfied_rows(run.prover) == 0, gadgets
 
 
@@ -96,7 +96,7 @@ def test_cli_fixture_prover_then_verifier(name, tmp_path):
     for ext in (".gadgets", ".inst", ".wtns"):
         shutil.copy(os.path.join(FX, name + ext), str(tmp_path / (name + ext)))
     stem = str(tmp_path / name)
-    nc = fe.prover_main(stem, seed=7, ext_rng32=b"\x17" * 32, ctx=ctx, label="fixtures/" + name)
+    nc = fe.prover_main(stem, test_seed=7, ext_rng32=b"\x17" * 32, ctx=ctx, label="fixtures/" + name)
     assert nc > 0
     assert os.path.getsize(stem + ".proof") % 32 == 1
     assert fe.verifier_main(stem, ctx=ctx, label="fixtures/" + name) is True
@@ -128,7 +128,7 @@ def test_cli_falsified_statements_are_rejected_and_oracle_agrees(tmp_path):
              ("OR\n[\n{\nEQUALS W0 W1\n}\n{\nLESS_THAN W1 W0\n}\n]\n", "", "W0 = 0x43\nW1 = 0x44\n", False),
              ("OR\n[\n{\nEQUALS W0 W1\n}\n{\nLESS_THAN W0 W1\n}\n]\n", "", "W0 = 0x43\nW1 = 0x44\n", True)]
     for k, (gadgets, inst, wtns, want) in enumerate(cases):
-        run = fe.ProverRun(b"case", gadgets, inst, wtns, seed=k, ctx=ctx)
+        run = fe.ProverRun(b"case", gadgets, inst, wtns, test_seed=k, ctx=ctx)
         coms, proof, _ = run.finish(ext_rng32=bytes([k]) * 32)
         vr = fe.VerifierRun(b"case", gadgets, inst, coms, ctx=ctx)
         assert vr.finish(proof) is want, gadgets

@@ -60,10 +60,10 @@ def main():
             shutil.copy(os.path.join(fx, "example" + ext), os.path.join(d, "example" + ext))
         stem = os.path.join(d, "example")
         ctx.gens_ensure(1 << 14)
-        fe.prover_main(stem, seed=1, ctx=ctx, label="example")
-        t_p, nc = timed(lambda: fe.prover_main(stem, seed=1, ctx=ctx, label="example"), 2)
+        fe.prover_main(stem, test_seed=1, ctx=ctx, label="example")
+        t_p, nc = timed(lambda: fe.prover_main(stem, test_seed=1, ctx=ctx, label="example"), 2)
         t_v, ok = timed(lambda: fe.verifier_main(stem, ctx=ctx, label="example"), 2)
-        prun = fe.ProverRun(b"example", open(stem + ".gadgets").read(), open(stem + ".inst").read(), open(stem + ".wtns").read(), seed=1, ctx=ctx)
+        prun = fe.ProverRun(b"example", open(stem + ".gadgets").read(), open(stem + ".inst").read(), open(stem + ".wtns").read(), test_seed=1, ctx=ctx)
         t_dev, _ = timed(lambda: prun.prover.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32)), 2)
         res["config0_example_cli"] = {"constraints": nc, "multipliers": prun.prover.get_num_multiplications(), "prover_cli_ms_incl_python_frontend": t_p,
                                       "verifier_cli_ms_incl_python_frontend": t_v, "prove_call_ms": t_dev, "verifier_prints": "true" if ok else "false"}
