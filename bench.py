@@ -4,25 +4,29 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-Metric (BASELINE.json): R1CS proofs/sec (and MSM Mpoints/sec in the `msm` sweep) on BASELINE configs[1]:
-"merkle_tree membership with mimc_hash, depth 32, single proof" (n = 63 180 multipliers, N = 2^16, m = 4).
-A proof = Pedersen commits, 3 commitment MSMs, polynomial phase, 16 IPP rounds of that circuit.  A step = K proofs, one
-per concurrent prover of the GPU (independent host thread + bpg_ctx each; K is reported in `config`); the K * steps
-proofs of the timed region are handed out to the free-running provers one at a time, which hides the sequential host-side
-Merlin RNG of one proof (its stream shares SIMD lanes with the other provers' streams) behind the device work of the
-others; `single_proof_latency_ms` is the un-overlapped figure.  Every rank runs its own provers (weak scaling, no data-path
-collective).  Extras for N > 1: `msm_sharded` (one MSM split by point range) and `one_proof_2p20` (ONE large proof split
-over the ranks, BASELINE configs[3]).
+Metric (BASELINE.json): R1CS proofs/sec (and MSM Mpoints/sec in the `msm*` sweeps) on BASELINE configs[3], the size
+north_star's target sentence names: "synthetic R1CS circuit 2^20 multipliers (MSM ~2^21 points, IPP 20 rounds)" --
+993 384 multipliers (the reference's own largest circuit, merkle_tree_gadget.rs:473-545), N = 2^20, byte-exact proofs.
+A proof = Pedersen commit, 3 commitment MSMs of 2n+1 / n+1 / 2n+1 points, polynomial phase, 20 IPP rounds.
+A step = P proofs, one per concurrent prover of the GPU (own host thread + bpg_ctx + witness each; P is in `config`);
+the P * steps proofs of the timed region are handed out to free-running provers, so the sequential host-side Merlin
+TranscriptRng of one proof (2n draws, ~0.7 s of one core at this size; the streams of concurrent provers share SIMD
+lanes) overlaps the device work of the others.  Every rank runs its own provers (weak scaling, no data-path collective).
 
-  value  proofs/s with the witness vectors already resident in HBM (BPG_FLAG_WITNESS_ON_DEVICE)
-  e2e    proofs/s through the C ABI with HOST buffers: witness H2D, proof + commitments D2H inside the timed region
-  roofline   the dominant kernel k_msm_accumulate (bucket accumulation of the fixed-base Pippenger): algorithmic bytes
-             = 100 B per (term, window) pair (96 B affine-Niels table entry + 4 B sorted index) / CUDA-event time
-  cpu_baseline   the C oracle (oracle/bpo.c, a restatement of dalek's algorithms) on the host cores, same circuit
+  value         proofs/s, witness vectors already resident in HBM (BPG_FLAG_WITNESS_ON_DEVICE)
+  e2e           proofs/s through the C ABI with HOST buffers: witness H2D, proof + commitments D2H inside the timed region
+  roofline      the dominant kernel k_msm_accumulate against what binds it, the integer-multiply pipe (measured MAC32/s of a
+                dependent field-multiply chain); the HBM view (100 B per (term, window) pair) is listed beside it
+  cpu_baseline  the C oracle (oracle/bpo.c, a restatement of dalek's algorithms) on the host cores, same circuit, and the
+                GPU's proof bytes are compared with the oracle's
+Extras: MSM sweeps 2^16..2^22 with the oracle's Mpoints/s beside every point, MiMC, BASELINE configs[1] and [4]
+(batch verification of 8192 set_membership / less_than proofs, sharded by rank, verdicts == oracle), and for N > 1 the
+oracle-parity checks of the sharded MSM and the sharded prover.
 
 The reference itself (Rust) cannot be built in this image; `--impl reference` times the oracle port.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,16 +36,24 @@ import time
 
 # the concurrent provers use one CUDA stream each: give every stream its own hardware work queue (default: 8 shared)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# (BPG_BLOCKING_SYNC=1 makes provers sleep instead of spin while they wait for the device; measured neutral at K <= cores)
 
 _emit = print
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = "merkle_tree membership with mimc_hash, depth 32, single proof"
-DEPTH = 32
-GENS_CAP = 1 << 16
+WORKLOAD = "synthetic R1CS circuit 2^20 multipliers (MSM ~2^21 points, IPP 20 rounds) at 1/2/4/8 GPUs"
+NBLOCKS = 1022            # absorbed MiMC blocks: 1022 * 972 = 993 384 multipliers
+GENS_CAP = 1 << 20
+REF_SAMPLE_DIV = 16       # reference arm: every step proves a 1/16-size circuit of the same family (bounded sample)
+DTYPE = "u32 limbs (GF(2^255-19), Z_l)"
+
+
+def config_dict():
+    """identical in both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "n_multipliers": NBLOCKS * 972, "padded_n": GENS_CAP, "commitments": 1,
+            "circuit": "one MiMC sponge over %d blocks, 2 multipliers per round (mimc_hash_gadget.rs:133-144)" % NBLOCKS,
+            "byte_exact": True}
 
 
 class ClockSampler(threading.Thread):
@@ -73,7 +85,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -97,104 +109,150 @@ def barrier_max(dist, local, value):
     return float(t.item())
 
 
-def oracle_prove_time(inst, threads, reps=1):
+def oracle_prove(inst, cap, ext, threads):
+    """-> (seconds, proof, V) of the CPU oracle prover (oracle/bpo.c) on `threads` OpenMP threads"""
     import oracle_lib as ol
     ol.lib().bpo_set_threads(threads)
     rp, tv, tc = inst["csr"]
     tcb = inst.setdefault("_tc_bytes", tc.tobytes() if hasattr(tc, "tobytes") else tc)
-    best, proof = None, None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        proof, V = ol.r1cs_prove(inst["label"], GENS_CAP, inst["aL"], inst["aR"], inst["aO"], inst["vals"], inst["blinds"], rp, tv, tcb, bytes(32))
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best, proof
+    t0 = time.perf_counter()
+    proof, V = ol.r1cs_prove(inst["label"], cap, inst["aL"], inst["aR"], inst["aO"], inst["vals"], inst["blinds"], rp, tv, tcb, ext)
+    return time.perf_counter() - t0, proof, V
 
 
 def run_reference(args):
-    """reference arm: the reference's CPU algorithm for the same path (oracle port; the Rust crate cannot be built here)"""
-    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    """Reference arm: the reference's CPU algorithm for the same path on the host cores (oracle port, OpenMP on all cores; the
+    Rust crate cannot be built here).  A complete 2^20 proof takes the oracle ~20 s on 16 cores, so every step is a bounded
+    sample: one complete proof of the SAME circuit family at 1/16 of the size (64 instead of 1022 MiMC blocks, N = 2^16);
+    proving cost is linear in the multiplier count (constant-time Straus commitments + per-element generator folds; the
+    Pippenger share only gets cheaper per point with size), so proofs/s at full size = sample proofs/s / (n_full / n_sample).
+    bench.py's own arm times ONE complete full-size oracle proof beside the GPU figure (cpu_baseline) as the calibration."""
+    rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from bulletproofs_gadgets_b200 import gadgets
-    cores = os.cpu_count() or 1
-    inst = gadgets.merkle_path_instance(DEPTH, trace_on_device=False)
     import oracle_lib as ol
-    ol.gens(0, GENS_CAP)  # BulletproofGens::new outside the timed steps, as for the GPU arm
+    cores = os.cpu_count() or 1
+    full = os.environ.get("BPG_REF_FULL") == "1"
+    nblk = NBLOCKS if full else NBLOCKS // REF_SAMPLE_DIV
+    inst = gadgets.mimc_chain_instance(nblk, trace_on_device=False)
+    cap = 1
+    while cap < inst["n"]:
+        cap *= 2
+    scale = (NBLOCKS * 972) / inst["n"]
+    ol.gens(0, cap)  # BulletproofGens::new outside the timed steps, as for the GPU arm
     for _ in range(args.warmup):
-        oracle_prove_time(inst, cores)
+        oracle_prove(inst, cap, bytes(32), cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_prove_time(inst, cores)
+        oracle_prove(inst, cap, bytes(32), cores)
     dt = time.perf_counter() - t0
-    v = args.steps / dt
+    v = args.steps / dt / scale
+    sample = ("every step = 1 complete oracle proof of a %d-multiplier circuit of the same family (N = %d), OpenMP on all host cores; "
+              "value = sample proofs/s / %.2f (cost linear in the multiplier count)" % (inst["n"], cap, scale)) if not full else \
+        "full workload: complete proofs of the 993 384-multiplier circuit, OpenMP on all host cores"
     line = {"impl": "reference", "metric": "r1cs_proofs_per_sec", "value": v, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (GF(2^255-19), Z_l)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_multipliers": inst["n"], "padded_n": GENS_CAP, "commitments": inst["m"]},
-            "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port",
-                             "sample": "full workload: %d complete proofs of the depth-32 circuit, OpenMP on all host cores" % args.steps},
+            "dtype": DTYPE, "data": "synthetic", "config": config_dict(),
+            "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(line))
 
 
-def msm_sweep(ctx, sizes, reps=5, dist="uniform"):
+# ----------------------------------------------------------------------------------------------------------------- MSM sweeps
+def cpu_msm_mpoints(n, dist_kind, cores):
+    """oracle (dalek's vartime Pippenger restated, OpenMP) Mpoints/s on the same kind of input, n capped so it stays ~seconds"""
+    import numpy as np
+    import oracle_lib as ol
+    rng = np.random.default_rng(1 if dist_kind == "uniform" else 2)
+    h = n // 2
+    if dist_kind == "uniform":
+        raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        raw[:, 31] &= 0x0F
+    else:
+        raw = np.zeros((n, 32), dtype=np.uint8)
+        raw[:, 0] = rng.integers(0, 2, size=n, dtype=np.uint8)
+    ol.lib().bpo_set_threads(cores)
+    ol.gens(0, h)
+    sG, sH = raw[:h].tobytes(), raw[h:2 * h].tobytes()
+    t0 = time.perf_counter()
+    out = ol.msm_gens(sG, sH, h, 0)
+    dt = time.perf_counter() - t0
+    return n / dt / 1e6, out, (sG, sH)
+
+
+def msm_sweep(ctx, sizes, reps=5, dist="uniform", cpu_sizes=(), cores=1):
     """MSM Mpoints/s over the resident generators with device-resident scalars (points = n/2 G + n/2 H).
-    dist = "uniform": 252-bit scalars (SURVEY 8d MSM-uniform); "bits": scalars in {0, 1} (MSM-bits, the range-proof shape:
-    half of the pairs vanish, the other half all land in bucket 1 of window 0)"""
+    dist = "uniform": 252-bit scalars (SURVEY 8d MSM-uniform); "bits": scalars in {0, 1} (MSM-bits, the range-proof shape).
+    For the sizes in cpu_sizes the oracle's vartime MSM runs on the same scalars: its Mpoints/s is listed beside the GPU's and
+    the compressed results must be equal."""
+    import ctypes as C
     import numpy as np
     out = {}
-    rng = np.random.default_rng(1 if dist == "uniform" else 2)
-    maxn = max(sizes)
-    if dist == "uniform":
-        raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
-        raw[:, 31] &= 0x0F  # < 2^252 < l : uniform reduced scalars
-    else:
-        raw = np.zeros((maxn, 32), dtype=np.uint8)
-        raw[:, 0] = rng.integers(0, 2, size=maxn, dtype=np.uint8)
-    d = ctx.dev_alloc(32 * maxn)
-    ctx.dev_upload(d, raw.tobytes())
-    import ctypes as C
     for n in sizes:
         h = n // 2
+        # the same stream as cpu_msm_mpoints (fresh generator per size so both sides see identical scalars)
+        r2 = np.random.default_rng(1 if dist == "uniform" else 2)
+        if dist == "uniform":
+            raw = r2.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            raw[:, 31] &= 0x0F
+        else:
+            raw = np.zeros((n, 32), dtype=np.uint8)
+            raw[:, 0] = r2.integers(0, 2, size=n, dtype=np.uint8)
+        d = ctx.dev_alloc(32 * n)
+        ctx.dev_upload(d, raw.tobytes())
         dG, dH = d, C.c_void_p(d.value + 32 * h)
-        ctx.msm_gens_dev(dG, dH, h, 0)  # warm-up (sizes exceed L2 only from 2^20 up; tables are re-gathered randomly)
+        got = ctx.msm_gens_dev(dG, dH, h, 0)  # warm-up (sizes exceed L2 only from 2^20 up; tables are re-gathered randomly)
         ctx.event_record(0)
         for _ in range(reps):
             ctx.msm_gens_dev(dG, dH, h, 0)
         ctx.event_record(1)
         ms = ctx.event_elapsed_ms(0, 1) / reps
         out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3}
-    ctx.dev_free(d)
+        if n in cpu_sizes:
+            cpu_mp, want, _ = cpu_msm_mpoints(n, dist, cores)
+            out[str(n)].update({"cpu_mpoints_per_s": cpu_mp, "cpu_cores": cores, "equals_oracle": got == want})
+        ctx.dev_free(d)
     return out
 
 
-def msm_var_sweep(ctx, sizes, reps=3):
+def msm_var_sweep(ctx, sizes, reps=3, cpu_sizes=(), cores=1):
     """SURVEY 8d MSM-var: variable-base MSM through the host-buffer entry point bpg_msm (n compressed points + n scalars
-    uploaded, decompressed, one windowed scalar multiplication per term, tree sum): the path of the verifier's own points"""
+    uploaded, decompressed, bucket method): the path of the verifier's own points.  Host-timed (the call is synchronous)."""
     import numpy as np
+    import oracle_lib as ol
     out = {}
     rng = np.random.default_rng(3)
     maxn = max(sizes)
-    G, H = ctx.gens_export(0, min(maxn, ctx.gens_capacity()))
-    pts = (G + H) * (1 + maxn * 32 // max(1, len(G + H)))
+    G, H = ctx.gens_export(0, min(maxn // 2, ctx.gens_capacity()))
+    pts = G + H
+    while len(pts) < 32 * maxn:
+        pts = pts + pts
     raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
     raw[:, 31] &= 0x0F
     sc = raw.tobytes()
     for n in sizes:
-        ctx.msm(sc[:32 * n], pts[:32 * n])
+        got = ctx.msm(sc[:32 * n], pts[:32 * n])
         t0 = time.perf_counter()
         for _ in range(reps):
             ctx.msm(sc[:32 * n], pts[:32 * n])
         ms = (time.perf_counter() - t0) * 1e3 / reps
         out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3}
+        if n in cpu_sizes:
+            ol.lib().bpo_set_threads(cores)
+            t0 = time.perf_counter()
+            want = ol.msm(sc[:32 * n], pts[:32 * n])
+            dt = time.perf_counter() - t0
+            out[str(n)].update({"cpu_mpoints_per_s": n / dt / 1e6, "cpu_cores": cores, "equals_oracle": got == want})
     return out
 
 
-def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5):
+def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5, parity_n=1 << 16):
     """ONE MSM of n points split by point range over the ranks (parallel.msm_gens_sharded): every rank
     sums its slice of the resident generators, the 128-byte partial points are all-gathered over NCCL and added on every rank.
-    Timed on the host around barrier + synchronize (the collective runs on torch's stream), max over ranks."""
+    Timed on the host around barrier + synchronize (the collective runs on torch's stream), max over ranks.
+    `oracle_parity`: at parity_n points rank 0 also runs the CPU oracle on the full scalar vectors; every rank's sharded
+    result must equal it (multi-GPU parity that the 1-GPU test box cannot show)."""
     import ctypes as C
     import numpy as np
     from bulletproofs_gadgets_b200 import parallel
@@ -203,7 +261,7 @@ def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5):
     ctx.gens_ensure(maxn // 2)
     rng = np.random.default_rng(7)
     dev = "cuda:%d" % local
-    for n in sizes:
+    for n in [parity_n] + list(sizes):
         h = n // 2
         lo, hi = parallel.shard_range(h, rank, world)
         raw = rng.integers(0, 256, size=(2 * h, 32), dtype=np.uint8)  # same stream on every rank: sG | sH
@@ -216,6 +274,18 @@ def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5):
         agree = parallel.allgather_bytes(first, dev)
         if any(a != first for a in agree):
             raise SystemExit("sharded MSM: ranks disagree on the result")
+        if n == parity_n and "oracle_parity" not in out:
+            want = first
+            if rank == 0:
+                import oracle_lib as ol
+                ol.lib().bpo_set_threads(os.cpu_count() or 1)
+                want = ol.msm_gens(raw[:h].tobytes(), raw[h:].tobytes(), h, 0)
+            want = parallel.allgather_bytes(want, dev)[0]
+            if want != first:
+                raise SystemExit("sharded MSM: result differs from the CPU oracle")
+            out["oracle_parity"] = {"points": n, "all_ranks_equal_oracle": True}
+            ctx.dev_free(d)
+            continue
         barrier_max(dist, local, 0.0)
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -226,21 +296,35 @@ def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5):
     return out
 
 
-def one_large_proof(bpg, gadgets, ctx, dist, local, world):
-    """BASELINE configs[3]: ONE proof of a 993 384-multiplier circuit (N = 2^20, 20 IPP rounds) on `world` GPUs -- strong scaling.
-    With world > 1 every MSM of the proof is cut by point range over the ranks (bpg_ctx_set_shard, parallel.enable_sharded_prover)
-    and the partial points are all-gathered by NCCL; all ranks return the same bytes (checked).  Device-side blinding, because the
-    2n sequential transcript-RNG draws of the byte-exact mode (0.7 s of one host core) are the same on every rank."""
+def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
+    """ONE proof of the headline circuit on `world` GPUs -- strong scaling.  With world > 1 every MSM of the proof is cut by point
+    range over the ranks (bpg_ctx_set_shard) and the partial points are all-gathered; all ranks return the same bytes (checked).
+    Latency is quoted with device-side blinding (the 2n sequential transcript-RNG draws of the byte-exact mode, ~0.7 s of one
+    host core, are the same on every rank and hide nothing here); `oracle_parity` proves byte-exactness of the sharded prover
+    against the CPU oracle on a mid-size circuit of the same family (rank 0 runs the oracle, every rank must match)."""
     from bulletproofs_gadgets_b200 import parallel
-    inst = gadgets.mimc_chain_instance(1022, ctx=ctx)
-    ctx.gens_ensure(1 << 20)
+    dev = "cuda:%d" % local
     circ = gadgets.Circuit(ctx, inst["n"], inst["m"], inst["csr"])
-    keep = parallel.enable_sharded_prover(ctx, "cuda:%d" % local) if world > 1 else None
+    keep = parallel.enable_sharded_prover(ctx, dev) if world > 1 else None
     FAST = bpg._lib.FLAG_FAST_BLINDING
     ext = b"\x44" * 32
+    res = {"n_multipliers": inst["n"], "padded_n": GENS_CAP, "gpus": world}
+    if world > 1:
+        mid = gadgets.mimc_chain_instance(24, seed=11, ctx=ctx)  # 23 328 multipliers, N = 2^15: late fold + sharded exchange paths
+        cm = gadgets.Circuit(ctx, mid["n"], mid["m"], mid["csr"])
+        got = cm.prove(mid, b"\x45" * 32)
+        want = got
+        if rank == 0:
+            _, p, V = oracle_prove(mid, 1 << 15, b"\x45" * 32, os.cpu_count() or 1)
+            want = (p, V)
+        wb = parallel.allgather_bytes(want[0] + want[1], dev)[0]
+        if wb != got[0] + got[1]:
+            raise SystemExit("sharded prover: proof bytes differ from the CPU oracle")
+        cm.close()
+        res["oracle_parity"] = {"n_multipliers": mid["n"], "all_ranks_equal_oracle": True}
     proof, V = circ.prove(inst, ext, FAST)  # warm-up (buffers, late-fold tables)
     if world > 1:
-        same = parallel.allgather_bytes(proof, "cuda:%d" % local)
+        same = parallel.allgather_bytes(proof, dev)
         if any(p != proof for p in same):
             raise SystemExit("sharded prover: ranks returned different proof bytes")
     if not circ.verify(inst["label"], V, proof):
@@ -252,20 +336,145 @@ def one_large_proof(bpg, gadgets, ctx, dist, local, world):
         circ.prove(inst, ext, FAST)
     ms = barrier_max(dist, local, (time.perf_counter() - t0) * 1e3 / reps)
     if world > 1:
-        ctx.check(ctx.lib.bpg_ctx_set_shard(ctx.h, 0, 1, None, None, 0, None, None))
+        parallel.disable_sharded_prover(ctx)
     del keep
     circ.close()
-    return {"n_multipliers": inst["n"], "padded_n": 1 << 20, "gpus": world, "prove_ms_fast_blinding": ms, "proofs_per_sec": 1e3 / ms,
-            "mode": "MSMs split by point range over the ranks, NCCL all-gather of the partial points" if world > 1 else "one GPU"}
+    res.update({"prove_ms_fast_blinding": ms, "proofs_per_sec": 1e3 / ms,
+                "mode": "MSMs split by point range over the ranks, all-gather of the partial points" if world > 1 else "one GPU"})
+    return res
 
 
+# ------------------------------------------------------------------------------------------------- BASELINE configs[4]
+def _cfg5_assemble(job):
+    """worker process (no CUDA): assemble one config-5 circuit through the front-end, return CSR + witness"""
+    kind, k, valid = job
+    import random
+    from bulletproofs_gadgets_b200 import frontend as fe
+    rnd = random.Random(60000 + k)
+    label = b"cfg5-%d" % k
+    if kind == "lt":
+        a, b = sorted(rnd.sample(range(1 << 56), 2))
+        if not valid:
+            a, b = b, a
+        run = fe.ProverRun(label, "LESS_THAN W0 W1\n", "", "W0 = 0x%014x\nW1 = 0x%014x\n" % (a, b), test_seed=k)
+    else:
+        vals = rnd.sample(range(1 << 40), 5)
+        member = vals[1 + k % 4] if valid else vals[0]
+        inst = "".join("I%d = 0x%010x\n" % (i, vals[1 + i]) for i in (0, 1, 2))
+        wt = "W0 = 0x%010x\nW1 = 0x%010x\n" % (member, vals[4])
+        run = fe.ProverRun(label, "SET_MEMBER W0 I0 W1 I1 I2\n", inst, wt, test_seed=k)
+    p = run.prover
+    enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
+    rp, tv, tc = p.csr()
+    return (k, label, p.num_vars, len(p.v), rp, tv, tc, enc(p.aL), enc(p.aR), enc(p.aO), enc(p.v), enc(p.v_blinding), valid)
+
+
+def batch_verify_config5(bpg, ctx, dist, local, rank, world, total, cores):
+    """BASELINE configs[4]: batch verification of `total` SET_MEMBER / LESS_THAN proofs (the shapes of the reference's
+    tests/resources/set_membership.*, less_than.*: set size 4 with 40-bit values, 56-bit comparisons), 1 % of the statements
+    false, sharded over the ranks (proof k -> rank k mod world, no collective; verdicts gathered at the end).
+    The circuits are assembled by the front-end driver (frontend.py, the restated gadget library), proved on this rank's GPU,
+    verified in batches of 64 by bpg_r1cs_verify_batch, and every verdict is compared with the CPU oracle verifier's."""
+    import ctypes as C
+    import multiprocessing as mp
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_lib as ol
+    from bulletproofs_gadgets_b200 import parallel
+    jobs = [("sm" if k % 2 == 0 else "lt", k, (k % 100) != 37) for k in range(total)]
+    mine = [j for j in jobs if j[1] % world == rank]
+    t0 = time.perf_counter()
+    nproc = max(1, min(16, cores // max(world, 1)))
+    with mp.get_context("spawn").Pool(nproc) as pool:
+        built = pool.map(_cfg5_assemble, mine, chunksize=32)
+    t_asm = time.perf_counter() - t0
+    ctx.gens_ensure(512)
+    nctx = 8
+    ctxs = [ctx] + [bpg.Context(local) for _ in range(nctx - 1)]
+    for c in ctxs:
+        c.gens_ensure(512)
+    items = [None] * len(built)
+
+    def prove_slice(ci):
+        c = ctxs[ci]
+        for idx in range(ci, len(built), nctx):
+            k, label, n, m, rp, tv, tc, aL, aR, aO, v, vb, valid = built[idx]
+            h = C.c_void_p()
+            c.check(c.lib.bpg_circuit_create(c.h, n, m, len(rp) - 1, (C.c_uint32 * len(rp))(*rp), (C.c_uint32 * max(1, len(tv)))(*tv), tc, C.byref(h)))
+            cap = 1 + 32 * (14 + 64 + 2)
+            proof, V = C.create_string_buffer(cap), C.create_string_buffer(32 * max(1, m))
+            ext = hashlib.sha256(b"cfg5 ext %d" % k).digest()
+            rc = c.lib.bpg_r1cs_prove(c.h, h, label, len(label), aL, aR, aO, v, vb, ext, 0, V, proof, cap)
+            if rc < 0:
+                c.check(rc)
+            items[idx] = (h, label, V.raw[:32 * m], proof.raw[:rc], os.urandom(32))
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(nctx) as tp:
+        list(tp.map(prove_slice, range(nctx)))
+    t_prove = time.perf_counter() - t0
+    # circuits were created on their prover's context; verification only needs the device, any context of it will do
+    B = 64
+
+    def verify_slice(ci):
+        c = ctxs[ci]
+        out = {}
+        for b0 in range(ci * B, len(items), nctx * B):
+            chunk = items[b0:b0 + B]
+            for j, acc in enumerate(c.verify_batch(chunk)):
+                out[b0 + j] = acc
+        return out
+
+    for c in ctxs:
+        c.sync()
+    barrier_max(dist, local, 0.0)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(nctx) as tp:
+        parts = list(tp.map(verify_slice, range(nctx)))
+    for c in ctxs:
+        c.sync()
+    t_verify = barrier_max(dist, local, time.perf_counter() - t0)
+    verdicts = {}
+    for p in parts:
+        verdicts.update(p)
+    # oracle verdicts for this rank's shard (CPU), then everything is gathered
+    ol.lib().bpo_set_threads(1)
+
+    def oracle_one(idx):
+        k, label, n, m, rp, tv, tc = built[idx][:7]
+        _, _, V, proof, _ = items[idx]
+        cap = 8
+        while cap < n:
+            cap *= 2
+        return ol.r1cs_verify(label, cap, n, V, rp, tv, tc, proof, bytes(32))
+
+    ol.gens(0, 512)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max(1, cores // max(world, 1))) as tp:
+        want = list(tp.map(oracle_one, range(len(built))))
+    t_oracle = time.perf_counter() - t0
+    local_pairs = [(built[i][0], bool(verdicts[i])) for i in range(len(built))]
+    all_gpu = parallel.gather_verdicts(local_pairs, total, "cuda:%d" % local if world > 1 else None)
+    all_cpu = parallel.gather_verdicts([(built[i][0], bool(want[i])) for i in range(len(built))], total, "cuda:%d" % local if world > 1 else None)
+    expected = [j[2] for j in jobs]
+    for it in items:
+        ctx.lib.bpg_circuit_destroy(it[0])
+    for c in ctxs[1:]:
+        c.close()
+    return {"proofs": total, "invalid": expected.count(False), "gpus": world, "verify_s": t_verify, "verifications_per_sec": total / t_verify,
+            "verdicts_match_oracle": all_gpu == all_cpu, "verdicts_match_expected": all_gpu == expected,
+            "batch": B, "contexts_per_gpu": nctx, "shapes": "SET_MEMBER (set of 4, 40-bit values, 8 multipliers) / LESS_THAN (56-bit values, 379 multipliers)",
+            "setup": {"assemble_s": t_asm, "gpu_prove_s": t_prove, "proofs_per_sec_proving": len(built) / t_prove, "oracle_verify_s": t_oracle,
+                      "oracle_verifications_per_sec": len(built) / t_oracle, "oracle_threads": max(1, cores // max(world, 1))}}
+
+
+# ------------------------------------------------------------------------------------------------------------ provers
 class ProverLane:
-    """one host thread's private context: own bpg_ctx (stream, workspace, tables), circuit copy and HBM-resident witness"""
+    """one host thread's private context: own bpg_ctx (stream, workspace), circuit copy, own witness (host + HBM-resident)"""
 
-    def __init__(self, bpg, gadgets, device, inst):
+    def __init__(self, bpg, gadgets, device, inst, cap):
         import ctypes as C
         self.ctx = bpg.Context(device)
-        self.ctx.gens_ensure(GENS_CAP)
+        self.ctx.gens_ensure(cap)
         self.inst = inst
         self.circ = gadgets.Circuit(self.ctx, inst["n"], inst["m"], inst["csr"])
         n = inst["n"]
@@ -283,125 +492,124 @@ class ProverLane:
         self.ctx.close()
 
 
-def run_ours(args):
-    from concurrent.futures import ThreadPoolExecutor
-    world, rank, local, dist = dist_setup(args.gpus)
-    import bulletproofs_gadgets_b200 as bpg
-    from bulletproofs_gadgets_b200 import gadgets
-    cores = os.cpu_count() or 1
-    per_gpu = cores / max(world, 1)
-    if args.provers > 0:
-        K = args.provers
-    else:
-        # The provers' bulk transcript-RNG draws are batched into SIMD lanes by the library (host_rng_service.h) and the waiting
-        # threads sleep, so the prover count is set by latency hiding, not by the core count: a proof spends ~60-100 ms in the
-        # shared RNG lanes and ~12 ms on the device, and ~300 proofs/s need ~30+ proofs in flight.
-        # Measured on one B200 + 16 cores: K = 24 / 48 / 64 / 96 / 128 -> 249 / 272 / 312 / 328 / 329 proofs/s byte-exact
-        # (fast blinding: 327-332, i.e. 96 provers close the gap).  With fewer than 8 cores per GPU the host is the limit and
-        # more threads do not help (8 GPUs on 32 cores were measured with 64).
-        K = 96 if per_gpu >= 8 else 64
-    # more prover threads than cores: they sleep while they wait for the device (bpg_set_blocking_sync); the solo latency
-    # measurements further down (single proof, MSM sweeps) switch back to spinning
-    blocking = K * world > cores
-    ctx0 = bpg.Context(local)
-    ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)
-    inst = gadgets.merkle_path_instance(DEPTH, seed=4 + rank, ctx=ctx0)
-    lanes = [ProverLane(bpg, gadgets, local, inst) for _ in range(K)]
-    ctx, circ, n = lanes[0].ctx, lanes[0].circ, inst["n"]
-    ext = bytes([rank + 1]) * 32
-    RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
+class LaneSet:
+    """P free-running provers on one GPU; timed(flags, resident, steps) runs P * steps proofs handed out one at a time"""
 
-    proof, V = circ.prove(inst, ext)
-    if not circ.verify(inst["label"], V, proof):
-        raise SystemExit("self-check failed: the verifier rejected the benchmark proof")
-    pool = ThreadPoolExecutor(max_workers=K)
+    def __init__(self, bpg, gadgets, device, insts, cap, rank):
+        from concurrent.futures import ThreadPoolExecutor
+        self.lanes = [ProverLane(bpg, gadgets, device, inst, cap) for inst in insts]
+        self.P = len(self.lanes)
+        self.pool = ThreadPoolExecutor(max_workers=self.P)
+        self.rank = rank
+        self.tickets = {"next": 0, "total": 0, "lock": threading.Lock()}
+        self.host_cpu_ms = 0.0
+        self.region = 0
 
-    def step_batch(flags, resident):
-        """one step = K independent proofs, one per host thread / context, all on this rank's GPU"""
-        outs = list(pool.map(lambda ln: ln.prove(ext, flags, resident), lanes))
-        return outs
+    def _ext(self, ticket):
+        # every proof of the run gets its own 32 bytes standing for the reference's thread_rng draw
+        return hashlib.sha256(b"bench ext %d %d %d" % (self.rank, self.region, ticket)).digest()
 
-    tickets = {"next": 0, "total": 0, "lock": threading.Lock()}
-
-    def lane_run(ln, flags, resident, steps):
-        # staggered start (inside the timed region): lane i begins i ms late so that the lanes' host-RNG and device phases
-        # interleave from the first proof on instead of all lanes hitting the CPU, then the GPU, in lockstep.
-        # The K * steps proofs of the region are handed out one at a time, so every lane stays busy until the last proofs
-        # are taken and the region does not end on a few straggling lanes.
-        time.sleep(0.001 * lanes.index(ln))
+    def _lane_run(self, ln, flags, resident):
+        time.sleep(0.001 * self.lanes.index(ln))  # staggered start (inside the timed region)
         while True:
-            with tickets["lock"]:
-                if tickets["next"] >= tickets["total"]:
+            with self.tickets["lock"]:
+                if self.tickets["next"] >= self.tickets["total"]:
                     return
-                tickets["next"] += 1
-            ln.prove(ext, flags, resident)
+                tk = self.tickets["next"]
+                self.tickets["next"] += 1
+            ln.prove(self._ext(tk), flags, resident)
 
-    host_cpu_ms = [0.0]
-
-    def timed(flags, resident, steps):
-        """K * steps proofs (`steps` per prover on average), the provers free-running with no barrier between steps, so one
-        lane's host-side transcript RNG overlaps the other lanes' device work.  The region is bracketed by a sync of every
-        context on both sides."""
-        for ln in lanes:
+    def timed(self, flags, resident, steps):
+        """-> (ms, launches).  The region is bracketed by a sync of every context on both sides; device time by CUDA events on
+        lane 0's stream, wall clock beside it, the larger of the two is reported."""
+        self.region += 1
+        for ln in self.lanes:
             ln.ctx.sync()
-        l0 = sum(ln.ctx.launch_count() for ln in lanes)
-        tickets["next"], tickets["total"] = 0, K * steps
+        l0 = sum(ln.ctx.launch_count() for ln in self.lanes)
+        self.tickets["next"], self.tickets["total"] = 0, self.P * steps
+        ctx = self.lanes[0].ctx
         ctx.event_record(2)
         c0 = os.times()
         t0 = time.perf_counter()
-        list(pool.map(lambda ln: lane_run(ln, flags, resident, steps), lanes))
-        for ln in lanes:
+        list(self.pool.map(lambda ln: self._lane_run(ln, flags, resident), self.lanes))
+        for ln in self.lanes:
             ln.ctx.sync()
         ctx.event_record(3)
         ms_dev = ctx.event_elapsed_ms(2, 3)
         wall = (time.perf_counter() - t0) * 1e3
         c1 = os.times()
-        host_cpu_ms[0] = 1e3 * ((c1.user - c0.user) + (c1.system - c0.system)) / (K * steps)  # this process: all prover threads
-        return max(ms_dev, wall), sum(ln.ctx.launch_count() for ln in lanes) - l0
+        self.host_cpu_ms = 1e3 * ((c1.user - c0.user) + (c1.system - c0.system)) / max(1, self.P * steps)
+        return max(ms_dev, wall), sum(ln.ctx.launch_count() for ln in self.lanes) - l0
 
-    # proofs from every lane are byte-identical (same transcript, same randomness): a cheap cross-context check
-    outs = step_batch(0, False)
-    if any(o != (proof, V) for o in outs):
-        raise SystemExit("concurrent contexts produced different proof bytes")
-    # untimed warm-up in exactly the shape of the timed region (free-running lanes).  At least 10 steps: the 16 host threads
-    # need ~1 s of load before the OS has spread them over the cores (measured: the first second runs 35 % slower)
-    warm_steps = max(args.warmup, 20)  # (10 steps = 2 s left the first timed region 10-25 % low in 2 of 8 runs)
+    def close(self):
+        self.pool.shutdown()
+        for ln in self.lanes:
+            ln.close()
+
+
+def run_ours(args):
+    world, rank, local, dist = dist_setup()
+    import bulletproofs_gadgets_b200 as bpg
+    from bulletproofs_gadgets_b200 import gadgets
+    cores = os.cpu_count() or 1
+    per_gpu = cores / max(world, 1)
+    # Concurrent provers per GPU: a 2^20 proof is ~55 ms of device work and ~0.1 s of (lane-shared) host RNG, so a handful of
+    # proofs in flight hide the host side; each prover holds ~1.3 GB of HBM workspace.
+    P = args.provers if args.provers > 0 else (8 if per_gpu >= 8 else 6)
+    blocking = P * world > cores
+    ctx0 = bpg.Context(local)
+    ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)
+    ctx0.gens_ensure(GENS_CAP)
+    t0 = time.perf_counter()
+    insts = gadgets.mimc_chain_instances(NBLOCKS, [5 + 1000 * rank + k for k in range(P)], ctx=ctx0)  # lane 0 of rank 0 = seed 5
+    setup_s = {"instances_s": time.perf_counter() - t0}
+    t0 = time.perf_counter()
+    lanes = LaneSet(bpg, gadgets, local, insts, GENS_CAP, rank)
+    setup_s["lanes_s"] = time.perf_counter() - t0
+    ctx, circ, inst, n = lanes.lanes[0].ctx, lanes.lanes[0].circ, insts[0], insts[0]["n"]
+    RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
+    FAST = bpg._lib.FLAG_FAST_BLINDING
+
+    ext0 = bytes(32)
+    proof0, V0 = circ.prove(inst, ext0)  # also the proof the oracle must reproduce (cpu_baseline leg)
+    if not circ.verify(inst["label"], V0, proof0):
+        raise SystemExit("self-check failed: the verifier rejected the benchmark proof")
+    if (proof0, V0) != lanes.lanes[0].prove(ext0, RES, True):
+        raise SystemExit("self-check failed: resident-witness proof differs from the host-buffer proof")
+
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()  # started before the warm-up: the first nvidia-smi invocations (cold NVML start) are slow and disturb the run
-    timed(RES, True, warm_steps)
+        sampler.start()  # started before the warm-up: the first nvidia-smi invocations (cold NVML start) are slow
+    lanes.timed(RES, True, args.warmup)  # W untimed steps in exactly the shape of the timed region
     sampler.samples.clear()
     ctx.prof_enable(True)
     barrier_max(dist, local, 0.0)
-    ms_value, launches = timed(RES, True, args.steps)
+    ms_value, launches = lanes.timed(RES, True, args.steps)
     ms_value = barrier_max(dist, local, ms_value)
-    cpu_ms_value = host_cpu_ms[0]
+    cpu_ms_value = lanes.host_cpu_ms
     nl_c, kms_c, pairs_c = ctx.prof_read()   # lane 0's launches inside the timed region: they share the GPU with the other lanes
     ctx.prof_enable(False)
     barrier_max(dist, local, 0.0)
-    ms_e2e, _ = timed(0, False, args.steps)
+    ms_e2e, _ = lanes.timed(0, False, args.steps)
     ms_e2e = barrier_max(dist, local, ms_e2e)
-    barrier_max(dist, local, 0.0)
-    ms_fast, _ = timed(RES | bpg._lib.FLAG_FAST_BLINDING, True, args.steps)
-    ms_fast = barrier_max(dist, local, ms_fast)
+    ms_fast = None
+    if not args.no_extras:
+        barrier_max(dist, local, 0.0)
+        ms_fast, _ = lanes.timed(RES | FAST, True, max(1, args.steps // 2))
+        ms_fast = barrier_max(dist, local, ms_fast) / max(1, args.steps // 2) * args.steps
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=10)
     ctx0.lib.bpg_set_blocking_sync(0)
-    # the same kernel timed alone (one prover, nothing else on the GPU): this is the figure the roofline fraction is quoted on
+    # the dominant kernel timed alone (one prover, nothing else on the GPU): this is the figure the roofline fraction is quoted on
     barrier_max(dist, local, 0.0)
     ctx.prof_enable(True)
     ctx.event_record(4)
-    for _ in range(3):
-        lanes[0].prove(ext, RES | bpg._lib.FLAG_FAST_BLINDING, True)  # device-side blinding: no 45 ms host RNG gap inside the events
+    lanes.lanes[0].prove(ext0, RES | FAST, True)  # device-side blinding: no host RNG gap inside the events
     ctx.event_record(5)
     solo_ms = ctx.event_elapsed_ms(4, 5)
-    # A proof launches the kernel at two very different sizes: the full-size MSMs over the resident generators (commitments,
-    # first IPP rounds, the late-fold materialisation: >= 1 M pairs each, > 95 % of the kernel's time) and the tiny ones over
-    # the 2 x 512 materialised generators (late IPP rounds, ~16 K pairs, launch-latency bound).  The roofline is quoted on the
-    # full-size launches; the small ones are listed beside it.
     per_launch = ctx.prof_read_launches()
-    ctx.prof_enable(False)  # never leave a daemon thread (mid nvidia-smi call) running into interpreter shutdown
+    ctx.prof_enable(False)
     big_cut = 0.25 * max([p for _, p in per_launch] or [0])
     big = [(m, p) for m, p in per_launch if p >= big_cut]
     small = [(m, p) for m, p in per_launch if p < big_cut]
@@ -409,58 +617,74 @@ def run_ours(args):
     small_launches = {"launches": len(small), "avg_launch_ms": (sum(m for m, _ in small) / len(small)) if small else None,
                       "pairs_per_launch": (sum(p for _, p in small) / len(small)) if small else None,
                       "share_of_kernel_time": (sum(m for m, _ in small) / max(sum(m for m, _ in per_launch), 1e-12)) if per_launch else None}
-    nproofs = world * K * args.steps
+    nproofs = world * P * args.steps
 
     extras = {}
     if rank == 0 and not args.no_extras:
-        # single-proof latency (one context, nothing else on the GPU), verification, fast-blinding, MSM sweep, MiMC, integer pipe
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            lanes[0].prove(ext, RES, True)
-        extras["single_proof_latency_ms"] = 1e3 * (time.perf_counter() - t0) / args.steps
-        ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)
-        list(pool.map(lambda ln: ln.circ.verify(inst["label"], V, proof), lanes))  # warm-up
+        lanes.lanes[0].prove(ext0, RES, True)
+        extras["single_proof_latency_ms"] = 1e3 * (time.perf_counter() - t0)
+        extras["single_proof_latency_ms_fast_blinding"] = solo_ms
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            list(pool.map(lambda ln: ln.circ.verify(inst["label"], V, proof), lanes))
-        extras["verify_per_sec"] = K * args.steps / (time.perf_counter() - t0)
-        ctx0.lib.bpg_set_blocking_sync(0)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            lanes[0].prove(ext, RES | bpg._lib.FLAG_FAST_BLINDING, True)
-        extras["single_proof_latency_ms_fast_blinding"] = 1e3 * (time.perf_counter() - t0) / args.steps
+        for _ in range(3):
+            circ.verify(inst["label"], V0, proof0)
+        extras["verify_ms"] = 1e3 * (time.perf_counter() - t0) / 3
         extras["single_warp_latency_cycles"] = ctx.bench_latency(200)
-        nh = 1 << 14
+        # MiMC (a10 / a11): independent Merkle nodes (2-block sponges), digests only and with the witness trace
+        nh = 1 << 16
         leaves = [[os.urandom(32), os.urandom(32)] for _ in range(nh)]
         ctx.mimc_sponge_batch(leaves[:64])
         t0 = time.perf_counter()
         ctx.mimc_sponge_batch(leaves)
-        extras["mimc_merkle_nodes_per_sec"] = nh / (time.perf_counter() - t0)
+        dt = time.perf_counter() - t0
+        mac_per_block = 972 * 136.0
+        extras["mimc"] = {"merkle_nodes": nh, "nodes_per_sec_e2e": nh / dt, "blocks_per_sec_e2e": 2 * nh / dt,
+                          "mac32_per_sec": 2 * nh * mac_per_block / dt,
+                          "note": "host-timed through bpg_mimc_sponge_batch (upload, kernel, download); 972 mod-l multiplications = 1.32e5 MAC32 per block"}
+        if hasattr(ctx, "mimc_bench"):
+            extras["mimc"].update(ctx.mimc_bench())
         sizes = [1 << k for k in range(16, 17 + 1)] if args.quick else [1 << k for k in range(16, 22 + 1)]
         if not args.quick:
             ctx.gens_ensure(1 << 21)
-        extras["msm"] = msm_sweep(ctx, sizes)
-        extras["msm_bits"] = msm_sweep(ctx, sizes, dist="bits")
-        extras["msm_var"] = msm_var_sweep(ctx, [1 << 10, 1 << 12] if args.quick else [1 << 10, 1 << 12, 1 << 14, 1 << 16])
+        cpu_sizes = (1 << 16,) if args.quick or args.no_cpu else (1 << 16, 1 << 18, 1 << 20, 1 << 22)
+        if args.no_cpu:
+            cpu_sizes = ()
+        extras["msm"] = msm_sweep(ctx, sizes, cpu_sizes=cpu_sizes, cores=cores)
+        extras["msm_bits"] = msm_sweep(ctx, sizes, dist="bits", cpu_sizes=cpu_sizes[:2], cores=cores)
+        vs = [1 << 10, 1 << 12] if args.quick else [1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 18, 1 << 20, 1 << 22]
+        extras["msm_var"] = msm_var_sweep(ctx, vs, cpu_sizes=() if args.no_cpu else ((1 << 12,) if args.quick else (1 << 16, 1 << 20)), cores=cores)
 
     if world > 1 and not args.no_extras:
         extras["msm_sharded"] = msm_sharded_sweep(ctx, dist, local, rank, world, [1 << 20] if args.quick else [1 << 20, 1 << 22])
-
     if not args.no_extras and not args.quick:
-        extras["one_proof_2p20"] = one_large_proof(bpg, gadgets, ctx, dist, local, world)
+        extras["one_proof_2p20"] = one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world)
 
+    # the full-size oracle proof beside the GPU's (rank 0, N = 1 only): ~20 s on 16 cores + BulletproofGens::new
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        t_cpu, proof_cpu = oracle_prove_time(dict(inst), cores)
-        proof_same, _ = circ.prove(inst, bytes(32))  # same transcript + randomness as the oracle run
+        import oracle_lib as ol
+        ol.lib().bpo_set_threads(cores)
+        t0 = time.perf_counter()
+        ol.gens(0, GENS_CAP)
+        t_gens = time.perf_counter() - t0
+        t_cpu, proof_cpu, V_cpu = oracle_prove(inst, GENS_CAP, ext0, cores)
         cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": cores, "kind": "port",
-               "sample": "1 complete proof of the same depth-32 circuit on all host cores (oracle/bpo.c, OpenMP)",
-               "proof_bytes_equal_gpu": proof_cpu == proof_same}
+               "sample": "1 complete proof of the same 993 384-multiplier circuit on all host cores (oracle/bpo.c, OpenMP), %.1f s; "
+                         "BulletproofGens::new(2^20) beside it: %.1f s" % (t_cpu, t_gens),
+               "proof_bytes_equal_gpu": (proof_cpu, V_cpu) == (proof0, V0)}
         if not args.quick:
-            # what the reference binary does today: one thread (SURVEY 8d asks for both figures)
-            t_one, proof_one = oracle_prove_time(dict(inst), 1)
-            cpu["single_thread_value"] = 1.0 / t_one
-            cpu["single_thread_bytes_equal"] = proof_one == proof_cpu
+            # what the reference binary does today: one thread -- on a 1/16-size circuit of the same family, scaled
+            small = gadgets.mimc_chain_instance(NBLOCKS // REF_SAMPLE_DIV, trace_on_device=False)
+            t_one, _, _ = oracle_prove(small, 1 << 16, ext0, 1)
+            cpu["single_thread_value"] = 1.0 / (t_one * NBLOCKS * 972 / small["n"])
+            cpu["single_thread_sample"] = "1 thread, %d-multiplier circuit, %.1f s, scaled by the multiplier count" % (small["n"], t_one)
+
+    lanes.close()  # free the 2^20 workspaces before the small-circuit extras
+
+    if not args.no_extras and not args.quick:
+        extras["batch_verify_8192"] = batch_verify_config5(bpg, ctx0, dist, local, rank, world, args.cfg5, cores)
+    if rank == 0 and not args.no_extras and not args.quick:
+        extras["config1_merkle_depth32"] = config1_throughput(bpg, gadgets, local, ctx0, cores, args)
 
     if rank == 0:
         peaks = {}
@@ -470,56 +694,75 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        achieved = (pairs * 100.0) / (kms * 1e-3) / 1e9 if kms > 0 else None
-        # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled to this run's pairs per launch
+        hbm_ach = (pairs * 100.0) / (kms * 1e-3) / 1e9 if kms > 0 else None
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_accumulate_traffic.json")) as f:
                 tj = json.load(f)
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_that_launch"] * (pairs / nl if nl else 0)
         except Exception:
             pass
-        # integer view of the same kernel: one mixed addition = 7 field multiplications = 504 32x32->64 multiply-accumulates;
-        # peak = the MAC32 rate a dependent fe_mul chain sustains at full occupancy on this GPU (bpg_bench_imad, measured below)
-        ms_i, mac = ctx.bench_imad(400)
+        # integer view: one mixed addition = 7 field multiplications = 504 32x32->64 multiply-accumulates;
+        # peak = the MAC32 rate a dependent fe_mul chain sustains at full occupancy on this GPU (bpg_bench_imad, measured here)
+        ms_i, mac = ctx0.bench_imad(400)
         imad_peak = mac / ms_i * 1e3
         imad_ach = pairs * 504.0 / (kms * 1e-3) if kms > 0 else None
         line = {"metric": "r1cs_proofs_per_sec", "value": nproofs / (ms_value * 1e-3), "unit": "proofs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": warm_steps, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), Z_l)", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "n_multipliers": n, "padded_n": GENS_CAP, "commitments": inst["m"],
-                           "constraints": int(len(inst["csr"][0]) - 1), "proofs_per_step_per_gpu": K,
-                           "concurrency": "%d independent provers per GPU (one host thread + one bpg_ctx each); a step is one proof per prover" % K,
-                           "l2": "window tables (201 MB at 2^16 capacity, one set per GPU shared by all provers) exceed the 126 MB L2", "byte_exact": True},
-                "e2e": {"value": nproofs / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": K * (3 * 32 * n + 2 * 32 * inst["m"] + 64 * n),
-                        "d2h_bytes_per_step": K * (len(proof) + 32 * inst["m"])},
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_dict(),
+                "run": {"proofs_per_step_per_gpu": P, "constraints": int(len(inst["csr"][0]) - 1),
+                        "concurrency": "%d independent provers per GPU (own host thread, bpg_ctx and witness each); a step is one proof per prover; "
+                                       "every proof has its own ext_rng32" % P,
+                        "l2": "window tables (3.2 GB at 2^20 capacity, one set per GPU shared by all provers) exceed the 126 MB L2",
+                        "setup_s": setup_s},
+                "e2e": {"value": nproofs / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": P * (3 * 32 * n + 2 * 32 * inst["m"] + 128 * n),
+                        "d2h_bytes_per_step": P * (len(proof0) + 32 * inst["m"])},
                 "gpu_launches": int(launches),
-                "proofs_per_sec_fast_blinding": nproofs / (ms_fast * 1e-3),
+                "proofs_per_sec_fast_blinding": (nproofs / (ms_fast * 1e-3)) if ms_fast else None,
                 "host_cores": cores, "host_cpu_ms_per_proof": cpu_ms_value,
-                "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "launches": int(nl),
+                "roofline": {"bound": "integer-multiply pipe (IMAD.WIDE); the contract's hbm view is listed as hbm_*", "kernel": "k_msm_accumulate",
+                             "achieved": imad_ach / 1e12 if imad_ach else None, "peak": imad_peak / 1e12, "unit": "TMAC32/s",
+                             "frac": (imad_ach / imad_peak) if imad_ach else None, "int_frac": (imad_ach / imad_peak) if imad_ach else None,
+                             "peak_note": "measured here: dependent field-multiply chain at full occupancy (bpg_bench_imad); 504 MAC32 per mixed addition",
+                             "hbm_achieved": hbm_ach, "hbm_peak": hbm_peak, "hbm_unit": "GB/s", "hbm_frac": (hbm_ach / hbm_peak) if hbm_ach else None,
+                             "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                             "traffic": traffic, "launches": int(nl),
                              "algorithmic_bytes_per_launch": (pairs / nl * 100.0) if nl else None,
                              "avg_launch_ms": kms / nl if nl else None, "pairs_per_launch": pairs / nl if nl else None,
-                             "note": "CUDA events around every full-size launch (>= 25 % of the largest pair count) of 3 proofs run alone after the timed region (kernel timed alone)",
+                             "note": "CUDA events on the library's stream around every full-size launch (>= 25 % of the largest pair count) of one proof run alone after the timed region",
                              "small_launches": small_launches,
                              "share_of_step": (sum(m for m, _ in per_launch) / solo_ms) if solo_ms > 0 else None,
-                             "share_note": "all k_msm_accumulate launches / device time of the same 3 solo proofs (compare profiles/r01_launch_summary_final.txt)",
+                             "share_note": "all k_msm_accumulate launches / device time of the same solo proof (compare profiles/r02_launch_summary_2p20.txt)",
                              "in_timed_region": {"launches": int(nl_c), "avg_launch_ms": kms_c / nl_c if nl_c else None,
-                                                 "note": "lane 0's launches while %d other provers share the GPU" % (K - 1)},
-                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                "imad_roofline": {"kernel": "k_msm_accumulate", "achieved": imad_ach, "peak": imad_peak, "unit": "MAC32/s",
-                                  "frac": (imad_ach / imad_peak) if imad_ach else None,
-                                  "note": "the kernel is integer-multiply bound before it is HBM bound; peak = measured dependent fe_mul chain"},
+                                                 "note": "lane 0's launches while %d other provers share the GPU" % (P - 1)}},
                 "cpu_baseline": cpu, "clocks": sampler.summary()}
         line.update(extras)
         _emit(json.dumps(line))
-    pool.shutdown()
-    for ln in lanes:
-        ln.close()
     ctx0.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config1_throughput(bpg, gadgets, local, ctx0, cores, args):
+    """BASELINE configs[1] (round 1's headline): Merkle membership, depth 32, n = 63 180, N = 2^16, byte-exact, many provers"""
+    P = 64
+    ctx0.lib.bpg_set_blocking_sync(1 if P > cores else 0)
+    inst = gadgets.merkle_path_instance(32, seed=4, ctx=ctx0)
+    lanes = LaneSet(bpg, gadgets, local, [inst] * P, 1 << 16, 0)
+    RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
+    lanes.timed(RES, True, 4)
+    ms, launches = lanes.timed(RES, True, 6)
+    res = {"workload": "merkle_tree membership with mimc_hash, depth 32, single proof", "n_multipliers": inst["n"], "provers": P,
+           "proofs_per_sec": P * 6 / (ms * 1e-3), "launches_per_proof": launches / (P * 6), "host_cpu_ms_per_proof": lanes.host_cpu_ms}
+    if not args.no_cpu:
+        t_cpu, proof_cpu, V_cpu = oracle_prove(dict(inst), 1 << 16, bytes(32), cores)
+        res["cpu_proofs_per_sec"] = 1.0 / t_cpu
+        res["cpu_cores"] = cores
+        res["proof_bytes_equal_oracle"] = (proof_cpu, V_cpu) == lanes.lanes[0].circ.prove(inst, bytes(32))
+    lanes.close()
+    ctx0.lib.bpg_set_blocking_sync(0)
+    return res
 
 
 def main():
@@ -531,11 +774,12 @@ def main():
         os.write(saved, (text + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--provers", type=int, default=0, help="concurrent provers (host threads / contexts) per GPU; 0 = auto")
-    ap.add_argument("--quick", action="store_true", help="small MSM sweep only")
+    ap.add_argument("--cfg5", type=int, default=8192, help="proofs in the batch-verification extra (BASELINE configs[4])")
+    ap.add_argument("--quick", action="store_true", help="small MSM sweep only, no config extras")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -232,44 +232,78 @@ def merkle_path_instance(depth, leaf=b"\x43", seed=4, ctx=None, label=b"merkle_p
         t = np.frombuffer(tr, dtype=np.uint8).reshape(n, 3, 32)
         aL, aR, aO = t[:, 0, :].tobytes(), t[:, 1, :].tobytes(), t[:, 2, :].tobytes()
     else:
-        aL, aR, aO = [], [], []
-        consts = round_constants()
-        for s in sponges:
-            st = 0
-            for b in s:
-                st = (st + b) % L_ORDER
-                for c in consts:
-                    tt = (st + c) % L_ORDER
-                    t2 = tt * tt % L_ORDER
-                    t3 = t2 * tt % L_ORDER
-                    aL += [tt, t2]; aR += [tt, tt]; aO += [t2, t3]
-                    st = t3
-        aL, aR, aO = _enc(aL), _enc(aR), _enc(aO)
+        aL, aR, aO = _mimc_trace_host(sponges)
     return dict(label=label, n=n, m=4, vals=_enc(vals), blinds=_enc(blinds), aL=aL, aR=aR, aO=aO, csr=csr.finish(), root=cur_val)
 
 
-def mimc_chain_instance(nblocks, seed=5, ctx=None, label=b"mimc_chain", trace_on_device=True):
+def _mimc_trace_host(sponges):
+    """(a_L, a_R, a_O) bytes of the MiMC chains in gadget order, host big-int (front-end / CPU-only callers)"""
+    aL, aR, aO = [], [], []
+    consts = round_constants()
+    for s in sponges:
+        st = 0
+        for b in s:
+            st = (st + b) % L_ORDER
+            for c in consts:
+                tt = (st + c) % L_ORDER
+                t2 = tt * tt % L_ORDER
+                t3 = t2 * tt % L_ORDER
+                aL += [tt, t2]; aR += [tt, tt]; aO += [t2, t3]
+                st = t3
+    return _enc(aL), _enc(aR), _enc(aO)
+
+
+def mimc_chain_instances(nblocks, seeds, ctx=None, label=b"mimc_chain", trace_on_device=True):
     """Synthetic circuit of `nblocks` absorbed MiMC blocks (972 multipliers each) in one long sponge; with
-    nblocks = 1022 this is the 2^20-multiplier class of BASELINE config 4 (993 384 multipliers, N = 2^20)."""
-    rng = np.random.default_rng(seed)
-    blocks = [int.from_bytes(rng.bytes(32), "little") & ((1 << 252) - 1) for _ in range(nblocks)]
-    digest = mimc_sponge_int(blocks) if nblocks <= 64 else None
-    vals = [blocks[0]]
-    blinds = [int.from_bytes(rng.bytes(64), "little") % L_ORDER]
+    nblocks = 1022 this is the 2^20-multiplier class of BASELINE configs[3] (993 384 multipliers, N = 2^20: the size of the
+    reference's ignored 512-leaf test, merkle_tree_gadget.rs:473-545).  One instance per seed: the committed first block
+    V_0 (and with it the whole witness trace and the digest constant of the last constraint) differs per seed, blocks
+    1.. are instance constants shared by all (seed 5's).  All traces come from ONE batched device call."""
+    base = np.random.default_rng(5)
+    blocks = [int.from_bytes(base.bytes(32), "little") & ((1 << 252) - 1) for _ in range(nblocks)]
     csr = _Csr()
     cur = csr.mimc_block([(_vid("V", 0), 1)])
     for b in blocks[1:]:
         cur = csr.mimc_block([(cur, 1), (_vid("1", 0), b)])
-    ctx = ctx or Context.default()
-    dig, tr = ctx.mimc_sponge_batch([[int(b).to_bytes(32, "little") for b in blocks]], trace=True)
-    dval = int.from_bytes(dig[0], "little")
-    if digest is not None:
-        assert dval == digest
-    csr.rows([[(cur, 1), (_vid("1", 0), (-dval) % L_ORDER)]])
+    csr.rows([[(cur, 1), (_vid("1", 0), 0)]])  # digest coefficient patched per instance below
     n = csr.nmul
-    t = np.frombuffer(tr, dtype=np.uint8).reshape(n, 3, 32)
-    return dict(label=label, n=n, m=1, vals=_enc(vals), blinds=_enc(blinds), aL=t[:, 0, :].tobytes(), aR=t[:, 1, :].tobytes(),
-                aO=t[:, 2, :].tobytes(), csr=csr.finish(), root=dval)
+    row_ptr, tv, tc = csr.finish()
+    firsts, blinds = [], []
+    for sd in seeds:
+        rng = np.random.default_rng(sd)
+        first = int.from_bytes(rng.bytes(32), "little") & ((1 << 252) - 1)
+        if sd == 5:
+            first = blocks[0]
+        firsts.append(first)
+        blinds.append(int.from_bytes(rng.bytes(64), "little") % L_ORDER)
+    sponges = [[f] + blocks[1:] for f in firsts]
+    if trace_on_device:
+        ctx = ctx or Context.default()
+        digs, tr = ctx.mimc_sponge_batch([[int(b).to_bytes(32, "little") for b in s] for s in sponges], trace=True)
+        t = np.frombuffer(tr, dtype=np.uint8).reshape(len(seeds), n, 3, 32)
+        traces = [(t[k, :, 0, :].tobytes(), t[k, :, 1, :].tobytes(), t[k, :, 2, :].tobytes()) for k in range(len(seeds))]
+        dvals = [int.from_bytes(d, "little") for d in digs]
+    else:
+        traces = [_mimc_trace_host([s]) for s in sponges]
+        dvals = [int.from_bytes(tr[2][-32:], "little") for tr in traces]
+    out = []
+    for k in range(len(seeds)):
+        tck = tc if k == len(seeds) - 1 else tc.copy()  # the last instance may keep the shared array
+        tck[-1, :] = np.frombuffer(((-dvals[k]) % L_ORDER).to_bytes(32, "little"), dtype=np.uint8)
+        aL, aR, aO = traces[k]
+        out.append(dict(label=label, n=n, m=1, vals=_enc([firsts[k]]), blinds=_enc([blinds[k]]), aL=aL, aR=aR, aO=aO,
+                        csr=(row_ptr, tv, tck), root=dvals[k]))
+    return out
+
+
+def mimc_chain_instance(nblocks, seed=5, ctx=None, label=b"mimc_chain", trace_on_device=True):
+    """one instance of mimc_chain_instances (seed 5: the round-1 benchmark witness)"""
+    inst = mimc_chain_instances(nblocks, [seed], ctx=ctx, label=label, trace_on_device=trace_on_device)[0]
+    if nblocks <= 64 and seed == 5:
+        base = np.random.default_rng(5)
+        blocks = [int.from_bytes(base.bytes(32), "little") & ((1 << 252) - 1) for _ in range(nblocks)]
+        assert inst["root"] == mimc_sponge_int(blocks)
+    return inst
 
 
 def bounds_check_batch_instance(count, nbytes=8, seed=5, label=b"bounds_batch", lo=0, hi=None, values=None):

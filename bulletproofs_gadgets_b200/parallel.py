@@ -109,3 +109,8 @@ def enable_sharded_prover(ctx, device):
     ctx.check(ctx.lib.bpg_ctx_set_shard(ctx.h, rank, world, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), _SHARD_CAP,
                                         C.cast(cb, C.c_void_p), None))
     return (send, recv, cb)
+
+
+def disable_sharded_prover(ctx):
+    """back to an unsharded prover on this context"""
+    ctx.check(ctx.lib.bpg_ctx_set_shard(ctx.h, 0, 1, None, None, 0, None, None))
