@@ -261,6 +261,7 @@ def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5, parity_n=1 <
     ctx.gens_ensure(maxn // 2)
     rng = np.random.default_rng(7)
     dev = "cuda:%d" % local
+    parallel.enable_comm(ctx, dev)  # the library's own NCCL communicator: the all-gather is enqueued on the context's stream
     for n in [parity_n] + list(sizes):
         h = n // 2
         lo, hi = parallel.shard_range(h, rank, world)
@@ -293,6 +294,8 @@ def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5, parity_n=1 <
         ms = barrier_max(dist, local, (time.perf_counter() - t0) * 1e3 / reps)
         out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3, "points_per_rank": 2 * (hi - lo)}
         ctx.dev_free(d)
+    parallel.disable_comm(ctx)
+    out["exchange"] = "ncclAllGather of the 128-byte partial points enqueued by libbpg on the context's stream (bpg_comm_init)"
     return out
 
 
@@ -305,7 +308,8 @@ def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
     from bulletproofs_gadgets_b200 import parallel
     dev = "cuda:%d" % local
     circ = gadgets.Circuit(ctx, inst["n"], inst["m"], inst["csr"])
-    keep = parallel.enable_sharded_prover(ctx, dev) if world > 1 else None
+    if world > 1:
+        parallel.enable_comm(ctx, dev)
     FAST = bpg._lib.FLAG_FAST_BLINDING
     ext = b"\x44" * 32
     res = {"n_multipliers": inst["n"], "padded_n": GENS_CAP, "gpus": world}
@@ -336,11 +340,10 @@ def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
         circ.prove(inst, ext, FAST)
     ms = barrier_max(dist, local, (time.perf_counter() - t0) * 1e3 / reps)
     if world > 1:
-        parallel.disable_sharded_prover(ctx)
-    del keep
+        parallel.disable_comm(ctx)
     circ.close()
     res.update({"prove_ms_fast_blinding": ms, "proofs_per_sec": 1e3 / ms,
-                "mode": "MSMs split by point range over the ranks, all-gather of the partial points" if world > 1 else "one GPU"})
+                "mode": "MSMs split by point range over the ranks; ncclAllGather of the partial points enqueued by libbpg on its own stream" if world > 1 else "one GPU"})
     return res
 
 

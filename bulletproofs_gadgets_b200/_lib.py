@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbpg.so")
 
-OK, E_CUDA, E_SIZE, E_DECOMPRESS, E_ARG, E_FORMAT, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OK, E_CUDA, E_SIZE, E_DECOMPRESS, E_ARG, E_FORMAT, E_NOMEM, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
 FLAG_LEGACY_FRAMING, FLAG_FAST_BLINDING, FLAG_WITNESS_ON_DEVICE = 1, 2, 4
 FLAG_NO_LATE_FOLD, FLAG_FORCE_LATE_FOLD = 8, 16
 
@@ -35,6 +35,10 @@ SYMBOLS = {
     "bpg_msm_gens_partial_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_points_sum_compress": (_i32, [_vp, _u8p, _sz, _u8p]),
     "bpg_ctx_set_shard": (_i32, [_vp, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
+    "bpg_comm_unique_id": (_i32, [_u8p]),
+    "bpg_comm_init": (_i32, [_vp, _i32, _i32, _u8p]),
+    "bpg_comm_destroy": (_i32, [_vp]),
+    "bpg_msm_gens_sharded_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _u8p]),
     "bpg_msm_gens_partial_to_dev": (_i32, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "bpg_points_sum_compress_dev": (_i32, [_vp, _vp, _sz, _u8p]),
     "bpg_fold_points": (_i32, [_vp, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]),

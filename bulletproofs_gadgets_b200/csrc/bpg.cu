@@ -70,6 +70,7 @@ extern "C" const char *bpg_strerror(int code) {
     case BPG_E_ARG: return "invalid argument";
     case BPG_E_FORMAT: return "proof format error";
     case BPG_E_NOMEM: return "out of memory";
+    case BPG_E_COMM: return "NCCL communicator error";
     }
     return "unknown";
 }
@@ -123,12 +124,13 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DSTEP("synced");
+    if (ctx->comm) bpg_comm_destroy(ctx);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     ctx->prof_ev.clear();
     DSTEP("prof events destroyed");
     // prover secrets (witness, blindings, transcript-RNG draws) do not outlive the context
     for (int i : {8, 9, 12, 13}) if (ctx->scratch[i].p) cudaMemset(ctx->scratch[i].p, 0, ctx->scratch[i].cap);
-    if (!ctx->h_raw.empty()) explicit_bzero(ctx->h_raw.data(), ctx->h_raw.size());
+    if (ctx->h_pinned) explicit_bzero(ctx->h_pinned, ctx->h_pinned_cap);
     ctx->gens.reset(); // the tables are freed with their last user
     ctx->tab = nullptr; ctx->comb = nullptr;
     DSTEP("tables freed");
@@ -136,6 +138,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     for (dev_buf *b : bufs) b->release();
     for (dev_buf &b : ctx->scratch) b.release();
     ctx->batch_gh.release();
+    ctx->vb_sums.release(); ctx->comm_recv.release();
     ctx->mat_pts.release(); ctx->mat_ext.release(); ctx->mat_tab.release(); ctx->heavy_part.release();
     DSTEP("buffers freed");
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -143,6 +146,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     DSTEP("pinned freed");
     for (int i = 0; i < 16; i++) if (ctx->tev[i]) { if (dbg) fprintf(stderr, "[bpg destroy] tev[%d]=%p\n", i, (void *)ctx->tev[i]); cudaEventDestroy(ctx->tev[i]); }
     DSTEP("timer events destroyed");
+    for (int i = 0; i < 2; i++) if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     DSTEP("events destroyed");
@@ -385,11 +389,18 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
     uint32_t total = 0;
     for (int i = 0; i < plan->nseg; i++) { plan->seg[i].start = total; total += plan->seg[i].n; }
     plan->total = total;
-    int G = plan->ngroups;
+    const int vb = plan->varbase ? 1 : 0;
+    const int Gout = plan->ngroups;
+    int G = vb ? 16 * Gout : Gout; // bucket groups: with variable points every window of an output is a group of its own
     msm_params P;
     memcpy(P.seg, plan->seg, sizeof(P.seg));
-    P.nseg = plan->nseg; P.total = total; P.ptotal = plan->tab ? plan->ptotal : ctx->ptotal;
+    P.nseg = plan->nseg; P.total = total; P.ptotal = plan->tab ? plan->ptotal : ctx->ptotal; P.varbase = (uint32_t)vb;
     const ge_an *tab = plan->tab ? plan->tab : ctx->tab;
+    ge *d_final = d_out;
+    if (vb) { // the bucket engine writes the window sums, k_msm_horner16 recombines them into d_final
+        CTX_TRY(ctx->vb_sums.ensure((size_t)G * sizeof(ge)));
+        d_out = (ge *)ctx->vb_sums.p;
+    }
     if (total <= BPG_SMALL_MSM_TERMS) {
         // Small MSM (late IPP rounds over the materialised generators, small circuits): the 2 x 2^15-bucket reduction below
         // would cost more than the accumulation.  Split every 16-bit digit into two 8-bit digits instead (two pairs per
@@ -402,8 +413,9 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
         CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
         k_small_reduce<<<2 * G, 128, 0, s>>>((const ge *)ctx->buckets.p, (ge *)ctx->lvlQ.p);
         KCHECK();
-        k_small_combine<<<1, 32, 0, s>>>((const ge *)ctx->lvlQ.p, (uint32_t)G, d_out);
+        k_small_combine<<<(G + 31) / 32, 32, 0, s>>>((const ge *)ctx->lvlQ.p, (uint32_t)G, d_out);
         KCHECK();
+        if (vb) { k_msm_horner16<<<(Gout + 31) / 32, 32, 0, s>>>(d_out, (uint32_t)Gout, d_final); KCHECK(); }
         return BPG_OK;
     }
     uint32_t nb = (uint32_t)G * BPG_NBP;
@@ -443,12 +455,91 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
     KCHECK();
     k_msm_combine<<<G, 32, 0, s>>>(out2, d_out);
     KCHECK();
+    if (vb) { k_msm_horner16<<<(Gout + 31) / 32, 32, 0, s>>>(d_out, (uint32_t)Gout, d_final); KCHECK(); }
+    return BPG_OK;
+}
+
+// ---------------------------------------------------------------- NCCL exchange of partial points (K10)
+// The library owns a communicator per sharded context and enqueues ncclAllGather on the context's OWN stream, between the
+// kernel that produced the partial points and the kernel that adds the world's partials: no host synchronisation, no
+// callback, ~35 exchanges per 2^20 proof cost their NVLink latency only.  NCCL is resolved at run time (dlopen of
+// libnccl.so.2: the copy already loaded by the host application -- e.g. torch's bundled one -- or the system one), so
+// libbpg has no link-time dependency on it and single-GPU users never load it.
+#include <dlfcn.h>
+#include <nccl.h>
+namespace {
+struct nccl_api {
+    void *h = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+nccl_api &nccl() {
+    static nccl_api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("BPG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm) continue;
+            a.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (a.h) break;
+        }
+        if (!a.h) return;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy;
+    });
+    return a;
+}
+} // namespace
+extern "C" int bpg_comm_unique_id(uint8_t out128[128]) {
+    if (!out128) return BPG_E_ARG;
+    if (!nccl().ok) return BPG_E_COMM;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return BPG_E_COMM;
+    static_assert(sizeof id == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return BPG_OK;
+}
+extern "C" int bpg_comm_destroy(bpg_ctx *ctx) {
+    if (!ctx) return BPG_E_ARG;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl().CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+        ctx->shard_rank = 0; ctx->shard_world = 1; ctx->shard_cap = 0;
+    }
+    return BPG_OK;
+}
+// collective: every rank of the group calls it with the id rank 0 obtained from bpg_comm_unique_id
+extern "C" int bpg_comm_init(bpg_ctx *ctx, int rank, int world, const uint8_t id128[128]) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return BPG_E_ARG;
+    if (!nccl().ok) { ctx->last_error = "libnccl.so.2 not found (set BPG_NCCL_LIB)"; return BPG_E_COMM; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    bpg_comm_destroy(ctx);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t c = nullptr;
+    ncclResult_t r = nccl().CommInitRank(&c, world, id, rank);
+    if (r != ncclSuccess) { ctx->last_error = std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "error"); return BPG_E_COMM; }
+    ctx->comm = c;
+    ctx->shard_rank = rank; ctx->shard_world = world;
+    ctx->shard_send = nullptr; ctx->shard_recv = nullptr; ctx->shard_fn = nullptr; ctx->shard_user = nullptr;
+    ctx->shard_cap = (size_t)1 << 40; // exchange buffers are the library's own and grow on demand
     return BPG_OK;
 }
 
 extern "C" int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send, void *d_recv, size_t send_cap, bpg_allgather_fn allgather, void *user) {
     if (!ctx || world < 1 || rank < 0 || rank >= world) return BPG_E_ARG;
     if (world > 1 && (!d_send || !d_recv || !allgather || send_cap < (256u << 10))) return BPG_E_ARG;
+    if (ctx->comm) bpg_comm_destroy(ctx);
     ctx->shard_rank = rank; ctx->shard_world = world;
     ctx->shard_send = d_send; ctx->shard_recv = d_recv; ctx->shard_cap = send_cap;
     ctx->shard_fn = allgather; ctx->shard_user = user;
@@ -464,6 +555,15 @@ static inline void shard_slice(uint32_t n, int rank, int world, uint32_t &lo, ui
 static int shard_exchange_sum(bpg_ctx *ctx, cudaStream_t s, ge *d_pts, uint32_t K) {
     size_t bytes = (size_t)K * sizeof(ge);
     if (bytes > ctx->shard_cap) return BPG_E_SIZE;
+    if (ctx->comm) { // stream-ordered: partials -> all-gather over NVLink -> sum, nothing waits on the host
+        CTX_TRY(ctx->comm_recv.ensure(bytes * (size_t)ctx->shard_world));
+        ncclResult_t r = nccl().AllGather(d_pts, ctx->comm_recv.p, bytes, ncclUint8, (ncclComm_t)ctx->comm, s);
+        if (r != ncclSuccess) { ctx->last_error = std::string("ncclAllGather: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "error"); return BPG_E_COMM; }
+        ctx->launches++;
+        k_sum_ranks<<<LAUNCH_1D(K, 64), 0, s>>>((const ge *)ctx->comm_recv.p, K, (uint32_t)ctx->shard_world, d_pts);
+        KCHECK();
+        return BPG_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(ctx->shard_send, d_pts, bytes, cudaMemcpyDeviceToDevice, s));
     SYNC_TRY(ctx, s);
     if (ctx->shard_fn(ctx->shard_user, bytes) != 0) { ctx->last_error = "all-gather callback failed"; return BPG_E_ARG; }
@@ -547,9 +647,24 @@ extern "C" int bpg_pedersen_commit(bpg_ctx *ctx, const uint8_t *v, const uint8_t
     return BPG_OK;
 }
 
-// variable-base part: decompress + per-term windowed scalar multiplication + tree sum -> d_out (1 point)
+// variable-base part -> d_out (1 point).  Few terms (the 13 + 2 lg N + m points of a proof): decompress + one windowed scalar
+// multiplication per thread + tree sum (latency of ONE scalar multiplication).  Many terms (bpg_msm, circuits with thousands
+// of commitments, batch verification): decompress to affine Niels + the bucket engine over the points themselves.
+#define BPG_VARBASE_BUCKET_TERMS 8192
 static int varbase_msm_dev(bpg_ctx *ctx, cudaStream_t s, const uint8_t *d_scalars, const uint8_t *d_points32, size_t k, ge *d_out, uint32_t *d_ok,
                            dev_buf &pts_buf, dev_buf &blk_buf) {
+    if (k >= BPG_VARBASE_BUCKET_TERMS) {
+        CTX_TRY(pts_buf.ensure((k + 1) * sizeof(ge_an)));
+        ge_an *pts = (ge_an *)pts_buf.p;
+        k_decompress_an_kernel<<<LAUNCH_1D(k, 128), 0, s>>>(d_points32, (uint32_t)k, pts, d_ok);
+        KCHECK();
+        msm_plan plan;
+        memset(&plan, 0, sizeof plan);
+        plan.ngroups = 1; plan.varbase = 1; plan.tab = pts; plan.ptotal = (uint32_t)k; plan.lean = bpg_lean_now();
+        msm_seg &g = plan.seg[plan.nseg++];
+        g.scalars = (const sc *)d_scalars; g.n = (uint32_t)k; g.p0 = 0; g.group = 0; g.reduce = 1;
+        return msm_run(ctx, s, &plan, d_out);
+    }
     CTX_TRY(pts_buf.ensure((k + 1) * sizeof(ge)));
     size_t nb = (k + 63) / 64;
     CTX_TRY(blk_buf.ensure(2 * (nb + 64) * sizeof(ge)));
@@ -562,7 +677,8 @@ static int varbase_msm_dev(bpg_ctx *ctx, cudaStream_t s, const uint8_t *d_scalar
 }
 
 static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const uint8_t *h_sG, const uint8_t *h_sH, size_t n, size_t offset,
-                         const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t *out32, uint8_t *out128, void *d_out128 = nullptr) {
+                         const uint8_t *extra_scalars, const uint8_t *extra_points32, size_t k, uint8_t *out32, uint8_t *out128, void *d_out128 = nullptr,
+                         bool exchange = false) {
     if (!ctx) return BPG_E_ARG;
     if (k && (!extra_scalars || !extra_points32)) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -594,6 +710,7 @@ static int msm_gens_impl(bpg_ctx *ctx, const void *d_sG, const void *d_sH, const
     if (nG) { msm_seg &g = plan.seg[plan.nseg++]; g.scalars = (const sc *)d_sG; g.n = (uint32_t)n; g.p0 = (uint32_t)offset; g.group = 0; g.reduce = host_scalars || true; }
     if (nH) { msm_seg &g = plan.seg[plan.nseg++]; g.scalars = (const sc *)d_sH; g.n = (uint32_t)n; g.p0 = (uint32_t)(ctx->cap + offset); g.group = 0; g.reduce = host_scalars || true; }
     CTX_TRY(msm_run(ctx, s, &plan, res));
+    if (exchange && ctx->shard_world > 1) CTX_TRY(shard_exchange_sum(ctx, s, res, 1)); // this rank's slice -> sum over the ranks
     size_t npts = 1;
     if (k) {
         CTX_TRY(varbase_msm_dev(ctx, s, d_es, d_ep, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
@@ -629,6 +746,11 @@ extern "C" int bpg_msm_gens_partial_dev(bpg_ctx *ctx, const void *d_sG, const vo
 extern "C" int bpg_msm_gens_partial_to_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n, size_t offset, void *d_out128) {
     if (!d_out128) return BPG_E_ARG;
     return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n, offset, nullptr, nullptr, 0, nullptr, nullptr, d_out128);
+}
+extern "C" int bpg_msm_gens_sharded_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n_local, size_t offset, uint8_t out32[32]) {
+    if (!ctx || !out32) return BPG_E_ARG;
+    if (ctx->shard_world > 1 && !ctx->comm) return BPG_E_ARG; // needs bpg_comm_init
+    return msm_gens_impl(ctx, d_sG, d_sH, nullptr, nullptr, n_local, offset, nullptr, nullptr, 0, out32, nullptr, nullptr, /*exchange=*/true);
 }
 extern "C" int bpg_points_sum_compress_dev(bpg_ctx *ctx, const void *d_ext128, size_t n, uint8_t out32[32]) {
     if (!ctx || !d_ext128 || !out32 || n == 0 || n > 64) return BPG_E_ARG;

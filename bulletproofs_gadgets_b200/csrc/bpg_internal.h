@@ -40,6 +40,8 @@ struct msm_plan {
     uint32_t ptotal;    // points per window of `tab`
     int shard;          // 1: with a sharded context (bpg_ctx_set_shard) every vector segment is cut by point range, this rank sums
                         //    its slice and the partial results are all-gathered and added (protocol drivers only)
+    int varbase;        // 1: `tab` holds `ptotal` variable points in affine-Niels form (no window tables): bucket method per window +
+                        //    Horner recombination (bpg_msm, the verifier's own points)
     int lean;           // 1: throughput sizing (long accumulate chunks, k_msm_rowcol_lean) -- set by the protocol drivers when
                         //    several proofs are in flight in this process (bpg_lean_now)
 };
@@ -77,14 +79,16 @@ struct bpg_ctx {
     dev_buf scratch[16];
     dev_buf batch_gh;         // batch verification: every proof's g | h scalars
     dev_buf heavy_part;       // segment sums of heavy buckets (k_msm_heavy)
+    dev_buf vb_sums;          // variable-base MSM: the 16 window sums of every group
     dev_buf mat_pts, mat_ext, mat_tab; // late fold: materialised G^(k) | H^(k), their window chain, their affine-Niels tables
     // one proof split over the ranks of a node (bpg_ctx_set_shard): exchange buffers and the caller's all-gather
     int shard_rank = 0, shard_world = 1;
     void *shard_send = nullptr, *shard_recv = nullptr; size_t shard_cap = 0;
     bpg_allgather_fn shard_fn = nullptr; void *shard_user = nullptr;
-    void *h_pinned = nullptr; size_t h_pinned_cap = 0;
-    std::vector<uint8_t> h_raw; // grow-only host staging of the raw transcript-RNG draws (an 8 MB malloc / free per proof
-                                // means mmap + page faults + munmap under the process-wide mm lock, 48 threads at a time)
+    void *comm = nullptr;     // ncclComm_t of a context sharded with bpg_comm_init (exchange on the context's stream)
+    dev_buf comm_recv;        // gathered partial points of all ranks
+    void *h_pinned = nullptr; size_t h_pinned_cap = 0; // two pinned staging buffers for the raw transcript-RNG draws (prover.inl)
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};      // upload of staging buffer b has completed
     cudaEvent_t tev[16] = {nullptr};
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev; // pairs (start, stop) around k_msm_accumulate

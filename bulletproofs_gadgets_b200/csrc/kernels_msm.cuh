@@ -27,6 +27,7 @@ struct msm_params {
     int nseg;
     uint32_t total;
     uint32_t ptotal;
+    uint32_t varbase; // 1: variable points (no window tables): entry = point index, window w of group g sums into group 16 g + w
 };
 
 // signed 16-bit digits: d in [-32768, 32767], sum d_w 2^(16w) = k  (k < 2^253 so the top digit never carries out)
@@ -84,11 +85,14 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
         if (S.alt) grp ^= ((j + S.j0) >> (S.alt - 1)) & 1u;
         pidx = S.p0 + j;
     }
-    uint32_t base = SPLIT ? grp * 2u * 129u : grp * BPG_NBP;
+    const uint32_t gstride = SPLIT ? 2u * 129u : BPG_NBP;
+    if (P.varbase) grp *= 16u;
+    uint32_t base = grp * gstride;
 #pragma unroll
     for (int w = 0; w < 16; w++) {
         int dw = d[w];
-        uint32_t ent = (uint32_t)w * P.ptotal + pidx;
+        uint32_t ent = P.varbase ? pidx : (uint32_t)w * P.ptotal + pidx;
+        if (P.varbase) base = (grp + (uint32_t)w) * gstride;
         if (SPLIT) {
             int dl = ((dw + 128) & 255) - 128; // [-128, 127]
             int dh = (dw - dl) >> 8;           // exact ; [-128, 128]
@@ -671,6 +675,37 @@ __global__ void __launch_bounds__(64) k_sum_ranks(const ge *__restrict__ recv, u
 #pragma unroll 1
     for (uint32_t r = 1; r < world; r++) { ld_ge(o, &recv[(size_t)r * K + k]); ge_add_ilp(acc, acc, o); }
     st_ge(&out[k], acc);
+}
+// ---- variable-base MSMs (bpg_msm, the verifier's own points): the same bucket engine with the 16 windows of a group as 16
+// bucket groups (no tables, entry = the point itself); this kernel recombines them:  out[g] = sum_w 2^(16 w) S[16 g + w]
+// (Horner from the top window: 240 doublings -- a fixed latency of every variable-base MSM; the points pay none).
+__global__ void __launch_bounds__(32) k_msm_horner16(const ge *__restrict__ S, uint32_t G, ge *__restrict__ out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    ge acc, t;
+    ld_ge(acc, &S[16 * g + 15]);
+#pragma unroll 1
+    for (int w = 14; w >= 0; w--) {
+#pragma unroll 1
+        for (int k = 0; k < 16; k++) ge_dbl(acc, acc);
+        ld_ge(t, &S[16 * g + w]);
+        ge_add(acc, acc, t);
+    }
+    st_ge(&out[g], acc);
+}
+// ristretto255 decode -> affine Niels (the decoded point is affine: Z = 1, T = x y); ok &= every encoding was valid
+__global__ void __launch_bounds__(128) k_decompress_an_kernel(const uint8_t *__restrict__ in32, uint32_t n, ge_an *__restrict__ out, uint32_t *ok) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    const uint4 *src = reinterpret_cast<const uint4 *>(in32 + 32ull * i);
+    uint4 v0 = src[0], v1 = src[1];
+    memcpy(b, &v0, 16); memcpy(b + 16, &v1, 16);
+    ge p;
+    if (!ristretto_decode(p, b)) { atomicAnd(ok, 0u); ge_identity(p); }
+    ge_an a;
+    ge_affine_to_an(a, p.X, p.Y);
+    st_an(&out[i], a);
 }
 __global__ void __launch_bounds__(128) k_sc_fill_one(sc *__restrict__ v, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -278,18 +278,37 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         tr.mark("rng(device)");
     } else {
         // The raw 64-byte draws come from the lane-batched RNG service (one Keccak-f per draw, shared SIMD registers with the
-        // other provers of this process); Scalar::from_bytes_mod_order_wide happens on the device.
-        std::vector<uint8_t> &raw = ctx->h_raw;
-        if (raw.size() < 128 * n + 64) raw.resize(128 * n + 64);
-        bpgh::RngService::get().draw64(rng, raw.data(), 2 * n);
-        tr.mark("rng");
+        // other provers of this process); Scalar::from_bytes_mod_order_wide happens on the device.  The stream is drawn in
+        // chunks into two pinned staging buffers and each chunk is uploaded while the next one is drawn: no pageable-memory
+        // staging copy by the driver (measured at n = 2^20: 128 MB per proof), and only 2 x 8 MB of secrets to wipe.
         if (n) {
+            const size_t CHUNK = (size_t)1 << 17; // draws per chunk (8 MB)
+            if (!ctx->h_pinned) {
+                CUDA_TRY(cudaHostAlloc(&ctx->h_pinned, 2 * CHUNK * 64, cudaHostAllocDefault));
+                ctx->h_pinned_cap = 2 * CHUNK * 64;
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming | cudaEventBlockingSync));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming | cudaEventBlockingSync));
+            }
             CTX_TRY(ctx->scratch[12].ensure((4 * N + 8) * sizeof(sc))); // l1|r0|r1|r3 later; free until the commit MSMs are done
-            CUDA_TRY(cudaMemcpyAsync(ctx->scratch[12].p, raw.data(), 128 * n, cudaMemcpyHostToDevice, s));
-            k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)ctx->scratch[12].p, (uint32_t)n, d_sL, d_sR);
+            uint8_t *d_raw = (uint8_t *)ctx->scratch[12].p;
+            size_t total = 2 * n, done = 0;
+            int used[2] = {0, 0};
+            for (size_t c = 0; done < total; c++) {
+                int b = (int)(c & 1);
+                size_t cnt = std::min(CHUNK, total - done);
+                uint8_t *hb = (uint8_t *)ctx->h_pinned + (size_t)b * CHUNK * 64;
+                if (used[b]) CUDA_TRY(cudaEventSynchronize(ctx->ev_stage[b])); // the previous upload from this buffer has finished
+                bpgh::RngService::get().draw64(rng, hb, cnt);
+                CUDA_TRY(cudaMemcpyAsync(d_raw + 64 * done, hb, 64 * cnt, cudaMemcpyHostToDevice, s));
+                CUDA_TRY(cudaEventRecord(ctx->ev_stage[b], s));
+                used[b] = 1;
+                done += cnt;
+            }
+            tr.mark("rng");
+            k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)d_raw, (uint32_t)n, d_sL, d_sR);
             KCHECK();
-            SYNC_TRY(ctx, s); // the staging buffer is reused by this context's next proof
-            explicit_bzero(raw.data(), 128 * n); // the raw draws are prover secrets (they determine s_L, s_R)
+            SYNC_TRY(ctx, s); // the staging buffers are reused by this context's next proof
+            explicit_bzero(ctx->h_pinned, std::min(ctx->h_pinned_cap, 64 * total)); // the raw draws are prover secrets (they determine s_L, s_R)
         }
     }
     memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
@@ -658,11 +677,14 @@ static int verify_finish(bpg_ctx *ctx, const std::vector<vprep *> &S, const std:
     ge *res = (ge *)ctx->results.p;
     uint32_t *d_ok = (uint32_t *)(res + 8);
     uint32_t one = 1, ok = 1;
-    CUDA_TRY(cudaMemcpyAsync(d_e, es.data(), 32 * k, cudaMemcpyHostToDevice, s2));
-    CUDA_TRY(cudaMemcpyAsync(d_e + 32 * k, ep.data(), 32 * k, cudaMemcpyHostToDevice, s2));
-    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s2));
-    CTX_TRY(varbase_msm_dev(ctx, s2, d_e, d_e + 32 * k, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
-    CUDA_TRY(cudaEventRecord(ctx->ev2, s2));
+    // few own points: per-term scalar multiplications on the second stream, concurrent with the fixed-base MSM;
+    // many (thousands of commitments, batches): the bucket engine, which shares this context's MSM workspace -> same stream
+    cudaStream_t vs = k >= BPG_VARBASE_BUCKET_TERMS ? s : s2;
+    CUDA_TRY(cudaMemcpyAsync(d_e, es.data(), 32 * k, cudaMemcpyHostToDevice, vs));
+    CUDA_TRY(cudaMemcpyAsync(d_e + 32 * k, ep.data(), 32 * k, cudaMemcpyHostToDevice, vs));
+    CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, vs));
+    CTX_TRY(varbase_msm_dev(ctx, vs, d_e, d_e + 32 * k, k, res + 1, d_ok, ctx->scratch[3], ctx->scratch[4]));
+    CUDA_TRY(cudaEventRecord(ctx->ev2, vs));
     const uint32_t pB = (uint32_t)(2 * ctx->cap);
     msm_plan plan;
     memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = 0;

@@ -38,6 +38,11 @@ def msm_gens_sharded(ctx, d_sG, d_sH, n, device=None):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(n, rank, world)
+    if world > 1 and id(ctx) in _COMM_CTX:
+        # the library's own communicator: partial MSM, all-gather, sum and compression are all enqueued on the context's stream
+        out = C.create_string_buffer(32)
+        ctx.check(ctx.lib.bpg_msm_gens_sharded_dev(ctx.h, d_sG, d_sH, hi - lo, lo, out))
+        return out.raw
     if world > 1 and device is not None and str(device).startswith("cuda"):
         # device-resident exchange: the 128-byte partial never leaves HBM; one NCCL all-gather, one 32-byte read-back
         import ctypes as C
@@ -76,6 +81,34 @@ def gather_verdicts(local, n_total, device=None):
         assert len(vals) == 1, "item %d owned by %d ranks" % (k, len(vals))
         res.append(vals.pop() == 2)
     return res
+
+
+# ---------------------------------------------------------------- in-library NCCL exchange (include/bpg.h: bpg_comm_init)
+_COMM_CTX = set()
+
+
+def enable_comm(ctx, device=None):
+    """Give `ctx` its own NCCL communicator over the ranks of the default process group (collective call).  From then on
+    bpg_r1cs_prove on this context is ONE proof split over the ranks and msm_gens_sharded() is one stream-ordered call: the
+    all-gather of the partial points is enqueued by the library on the context's stream (no host synchronisation per exchange).
+    torch.distributed only carries the 128-byte NCCL unique id."""
+    import ctypes as C
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        return False
+    uid = C.create_string_buffer(128)
+    if rank == 0:
+        ctx.check(ctx.lib.bpg_comm_unique_id(uid))
+    uid_bytes = allgather_bytes(uid.raw, device)[0]
+    ctx.check(ctx.lib.bpg_comm_init(ctx.h, rank, world, uid_bytes))
+    _COMM_CTX.add(id(ctx))
+    return True
+
+
+def disable_comm(ctx):
+    ctx.check(ctx.lib.bpg_comm_destroy(ctx.h))
+    _COMM_CTX.discard(id(ctx))
 
 
 # ---------------------------------------------------------------- one proof over several ranks (BASELINE configs[3])

@@ -31,6 +31,7 @@ extern "C" {
 #define BPG_E_ARG (-4)         /* null / inconsistent argument */
 #define BPG_E_FORMAT (-5)      /* R1CSProof::from_bytes failure (R1CSError::FormatError) */
 #define BPG_E_NOMEM (-6)
+#define BPG_E_COMM (-7)        /* NCCL not available / communicator error */
 
 typedef struct bpg_ctx bpg_ctx;
 typedef struct bpg_circuit bpg_circuit;
@@ -97,6 +98,18 @@ int bpg_points_sum_compress(bpg_ctx *ctx, const uint8_t *ext128, size_t n, uint8
  * world = 1 switches it off. */
 typedef int (*bpg_allgather_fn)(void *user, size_t bytes_per_rank);
 int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send, void *d_recv, size_t send_cap, bpg_allgather_fn allgather, void *user);
+
+/* The same sharding with the exchange INSIDE the library (SURVEY 8b bpg_comm_init): the context owns an NCCL communicator and
+ * enqueues ncclAllGather of the partial points on its own stream between the producing kernel and the summing kernel -- no host
+ * synchronisation, no callback.  NCCL is resolved at run time (dlopen libnccl.so.2; BPG_NCCL_LIB overrides the name).
+ * Rank 0 calls bpg_comm_unique_id and distributes the 128 bytes (any channel); then EVERY rank calls bpg_comm_init (collective).
+ * Afterwards bpg_r1cs_prove on these contexts is one proof over `world` GPUs exactly as with bpg_ctx_set_shard, and
+ * bpg_msm_gens_sharded_dev is one MSM split by point range: d_sG / d_sH point at this rank's slice (n_local terms starting at
+ * generator `offset`), every rank returns the same 32 bytes. */
+int bpg_comm_unique_id(uint8_t out128[128]);
+int bpg_comm_init(bpg_ctx *ctx, int rank, int world, const uint8_t id128[128]);
+int bpg_comm_destroy(bpg_ctx *ctx);
+int bpg_msm_gens_sharded_dev(bpg_ctx *ctx, const void *d_sG, const void *d_sH, size_t n_local, size_t offset, uint8_t out32[32]);
 
 /* the same two steps with the 128-byte partial points staying on the device, for callers whose collective runs there
  * (NCCL all-gather of the partials through torch.distributed): the partial is written to d_out128 (complete when the

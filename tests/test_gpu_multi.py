@@ -36,8 +36,11 @@ def _worker(rank, world, port, n, sG, sH, want, q):
         dG, dH = ctx.dev_alloc(32 * (hi - lo)), ctx.dev_alloc(32 * (hi - lo))
         ctx.dev_upload(dG, sG[32 * lo:32 * hi])
         ctx.dev_upload(dH, sH[32 * lo:32 * hi])
-        got = parallel.msm_gens_sharded(ctx, dG, dH, n, device="cuda:%d" % rank)
-        q.put((rank, got == want))
+        got = parallel.msm_gens_sharded(ctx, dG, dH, n, device="cuda:%d" % rank)  # torch all-gather of the partial points
+        parallel.enable_comm(ctx, "cuda:%d" % rank)                              # the library's own NCCL communicator
+        got2 = parallel.msm_gens_sharded(ctx, dG, dH, n, device="cuda:%d" % rank)
+        parallel.disable_comm(ctx)
+        q.put((rank, got == want and got2 == want))
         ctx.close()
     finally:
         dist.destroy_process_group()
@@ -78,14 +81,19 @@ def _shard_worker(rank, world, port, nmul, seed, want, q):
     try:
         ctx = bpg.Context(rank)
         ctx.gens_ensure(4096)
-        keep = parallel.enable_sharded_prover(ctx, "cuda:%d" % rank)
         inst = circuits.chain_instance(nmul, seed)
         ok = True
-        for flags in (lb.FLAG_FORCE_LATE_FOLD, lb.FLAG_NO_LATE_FOLD):
-            got = tr.gpu_prove(ctx, inst, bytes(range(32)), flags)
-            ok = ok and got == want
+        for mode in ("callback", "comm"):  # caller-supplied all-gather (bpg_ctx_set_shard) / in-library NCCL (bpg_comm_init)
+            keep = parallel.enable_sharded_prover(ctx, "cuda:%d" % rank) if mode == "callback" else parallel.enable_comm(ctx, "cuda:%d" % rank)
+            for flags in (lb.FLAG_FORCE_LATE_FOLD, lb.FLAG_NO_LATE_FOLD):
+                got = tr.gpu_prove(ctx, inst, bytes(range(32)), flags)
+                ok = ok and got == want
+            if mode == "callback":
+                parallel.disable_sharded_prover(ctx)
+            else:
+                parallel.disable_comm(ctx)
+            del keep
         q.put((rank, ok))
-        del keep
         ctx.close()
     finally:
         dist.destroy_process_group()
