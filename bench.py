@@ -660,7 +660,10 @@ def run_ours(args):
     if world > 1 and not args.no_extras:
         extras["msm_sharded"] = msm_sharded_sweep(ctx, dist, local, rank, world, [1 << 20] if args.quick else [1 << 20, 1 << 22])
     if not args.no_extras and not args.quick:
-        extras["one_proof_2p20"] = one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world)
+        # every rank must hold the SAME instance here (the lanes' witnesses differ per rank): seed 5 = rank 0's lane 0
+        shared = inst if rank == 0 else gadgets.mimc_chain_instance(NBLOCKS, seed=5, ctx=ctx0)
+        extras["one_proof_2p20"] = one_large_proof(bpg, gadgets, ctx, shared, dist, local, rank, world)
+        del shared
 
     # the full-size oracle proof beside the GPU's (rank 0, N = 1 only): ~20 s on 16 cores + BulletproofGens::new
     cpu = None

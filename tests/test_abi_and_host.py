@@ -25,6 +25,47 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(bpg._lib.SYMBOLS), declared ^ set(bpg._lib.SYMBOLS)
 
 
+def _c_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "bpg.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\n\s*[A-Za-z_][A-Za-z0-9_ \*]*?\b(bpg_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", h)
+    out = []
+    for name, args in protos:
+        args = " ".join(args.split())
+        out.append((name, 0 if args in ("", "void") else args.count(",") + 1))
+    return out
+
+
+def test_rust_ffi_matches_header():
+    """shim/src/ffi.rs (the reference-side binding) declares exactly the prototypes of include/bpg.h: same names,
+    same order, same arity, pointer-ness of every parameter, and the same constants.  No Rust toolchain exists in this image, so
+    the check is textual; shim/build.rs must build the same sources the Makefile builds."""
+    ffi = open(os.path.join(ROOT, "shim", "src", "ffi.rs")).read()
+    rust = re.findall(r"pub fn (bpg_[a-z0-9_]+)\((.*?)\)(?: -> [^;]+)?;", ffi)
+    c = _c_prototypes()
+    assert [n for n, _ in rust] == [n for n, _ in c]
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bpg.h")).read(), flags=re.S)
+    for (name, args), (_, arity) in zip(rust, c):
+        params = [a for a in args.split(", ") if a]
+        assert len(params) == arity, name
+        cargs = re.search(name + r"\s*\(([^;]*?)\)\s*;", hdr).group(1)
+        cparams = [a.strip() for a in " ".join(cargs.split()).split(",")] if arity else []
+        for rp, cp in zip(params, cparams):
+            is_ptr_c = "*" in cp or "[" in cp or "bpg_allgather_fn" in cp
+            is_ptr_r = "*" in rp or "Option<" in rp
+            assert is_ptr_c == is_ptr_r, (name, rp, cp)
+    for cname, val in re.findall(r"#define (BPG_[A-Z_]+) \(?(-?\d+)u?\)?", open(os.path.join(ROOT, "include", "bpg.h")).read()):
+        m = re.search(r"pub const %s: [iu]32 = (-?\d+);" % cname, ffi)
+        assert m and int(m.group(1)) == int(val), cname
+    build_rs = open(os.path.join(ROOT, "shim", "build.rs")).read()
+    mk = open(os.path.join(ROOT, "bulletproofs_gadgets_b200", "csrc", "Makefile")).read()
+    for token in ("arch=compute_100a,code=sm_100a", "bpg.cu", "host_keccak_lanes.cpp", "-ldl"):
+        assert token in build_rs and token in mk, token
+    lib_rs = open(os.path.join(ROOT, "shim", "src", "lib.rs")).read()
+    for used in set(re.findall(r"ffi::(bpg_[a-z0-9_]+)", lib_rs)):
+        assert used in [n for n, _ in c], used
+
+
 def test_no_cpu_fallback_without_device():
     import torch
 
