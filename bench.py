@@ -7,7 +7,8 @@
 Metric (BASELINE.json): R1CS proofs/sec (and MSM Mpoints/sec in the `msm*` sweeps) on BASELINE configs[3], the size
 north_star's target sentence names: "synthetic R1CS circuit 2^20 multipliers (MSM ~2^21 points, IPP 20 rounds)" --
 993 384 multipliers (the reference's own largest circuit, merkle_tree_gadget.rs:473-545), N = 2^20, byte-exact proofs.
-A proof = Pedersen commit, 3 commitment MSMs of 2n+1 / n+1 / 2n+1 points, polynomial phase, 20 IPP rounds.
+The circuit is the reference's test_merkle_tree_gadget_512: MerkleTree256 over 512 committed leaves (511 two-block MiMC nodes).
+A proof = 512 Pedersen commits, 3 commitment MSMs of 2n+1 / n+1 / 2n+1 points, polynomial phase, 20 IPP rounds.
 A step = P proofs, one per concurrent prover of the GPU (own host thread + bpg_ctx + witness each; P is in `config`);
 the P * steps proofs of the timed region are handed out to free-running provers, so the sequential host-side Merlin
 TranscriptRng of one proof (2n draws, ~0.7 s of one core at this size; the streams of concurrent provers share SIMD
@@ -43,16 +44,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOAD = "synthetic R1CS circuit 2^20 multipliers (MSM ~2^21 points, IPP 20 rounds) at 1/2/4/8 GPUs"
-NBLOCKS = 1022            # absorbed MiMC blocks: 1022 * 972 = 993 384 multipliers
+NLEAVES = 512             # the reference's largest circuit: 512-leaf MiMC Merkle tree, 511 nodes x 1944 = 993 384 multipliers
+N_MULT = (NLEAVES - 1) * 1944
 GENS_CAP = 1 << 20
-REF_SAMPLE_DIV = 16       # reference arm: every step proves a 1/16-size circuit of the same family (bounded sample)
+REF_SAMPLE_LEAVES = 32    # reference arm: every step proves the 32-leaf tree of the same family (31 nodes, N = 2^16): bounded sample
 DTYPE = "u32 limbs (GF(2^255-19), Z_l)"
 
 
 def config_dict():
     """identical in both arms (the driver compares them)"""
-    return {"workload": WORKLOAD, "n_multipliers": NBLOCKS * 972, "padded_n": GENS_CAP, "commitments": 1,
-            "circuit": "one MiMC sponge over %d blocks, 2 multipliers per round (mimc_hash_gadget.rs:133-144)" % NBLOCKS,
+    return {"workload": WORKLOAD, "n_multipliers": N_MULT, "padded_n": GENS_CAP, "commitments": NLEAVES,
+            "circuit": "MerkleTree256 over %d committed leaves, library API: the reference's test_merkle_tree_gadget_512 "
+                       "(merkle_tree_gadget.rs:473-545, BulletproofGens::new(1048576, 1))" % NLEAVES,
             "byte_exact": True}
 
 
@@ -123,7 +126,7 @@ def oracle_prove(inst, cap, ext, threads):
 def run_reference(args):
     """Reference arm: the reference's CPU algorithm for the same path on the host cores (oracle port, OpenMP on all cores; the
     Rust crate cannot be built here).  A complete 2^20 proof takes the oracle ~20 s on 16 cores, so every step is a bounded
-    sample: one complete proof of the SAME circuit family at 1/16 of the size (64 instead of 1022 MiMC blocks, N = 2^16);
+    sample: one complete proof of the SAME circuit family at 1/16 of the size (the 32-leaf instead of the 512-leaf tree, N = 2^16);
     proving cost is linear in the multiplier count (constant-time Straus commitments + per-element generator folds; the
     Pippenger share only gets cheaper per point with size), so proofs/s at full size = sample proofs/s / (n_full / n_sample).
     bench.py's own arm times ONE complete full-size oracle proof beside the GPU figure (cpu_baseline) as the calibration."""
@@ -134,12 +137,11 @@ def run_reference(args):
     import oracle_lib as ol
     cores = os.cpu_count() or 1
     full = os.environ.get("BPG_REF_FULL") == "1"
-    nblk = NBLOCKS if full else NBLOCKS // REF_SAMPLE_DIV
-    inst = gadgets.mimc_chain_instance(nblk, trace_on_device=False)
+    inst = gadgets.merkle_tree_instances(NLEAVES if full else REF_SAMPLE_LEAVES, [None], trace_on_device=False)[0]
     cap = 1
     while cap < inst["n"]:
         cap *= 2
-    scale = (NBLOCKS * 972) / inst["n"]
+    scale = N_MULT / inst["n"]
     ol.gens(0, cap)  # BulletproofGens::new outside the timed steps, as for the GPU arm
     for _ in range(args.warmup):
         oracle_prove(inst, cap, bytes(32), cores)
@@ -314,7 +316,7 @@ def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
     ext = b"\x44" * 32
     res = {"n_multipliers": inst["n"], "padded_n": GENS_CAP, "gpus": world}
     if world > 1:
-        mid = gadgets.mimc_chain_instance(24, seed=11, ctx=ctx)  # 23 328 multipliers, N = 2^15: late fold + sharded exchange paths
+        mid = gadgets.merkle_tree_instances(16, [11], ctx=ctx)[0]  # 29 160 multipliers, N = 2^15: late fold + sharded exchange paths
         cm = gadgets.Circuit(ctx, mid["n"], mid["m"], mid["csr"])
         got = cm.prove(mid, b"\x45" * 32)
         want = got
@@ -326,6 +328,15 @@ def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
             raise SystemExit("sharded prover: proof bytes differ from the CPU oracle")
         cm.close()
         res["oracle_parity"] = {"n_multipliers": mid["n"], "all_ranks_equal_oracle": True}
+    # the witness is made resident first (as for `value`): the strong-scaling figure is the device path, not a replicated H2D copy
+    import ctypes as C
+    n = inst["n"]
+    d_w = ctx.dev_alloc(3 * 32 * n)
+    ctx.dev_upload(d_w, inst["aL"] + inst["aR"] + inst["aO"])
+    host_inst = inst
+    inst = dict(inst)
+    inst["aL"], inst["aR"], inst["aO"] = (C.cast(C.c_void_p(d_w.value + 32 * n * k), C.c_char_p) for k in range(3))
+    FAST |= bpg._lib.FLAG_WITNESS_ON_DEVICE
     proof, V = circ.prove(inst, ext, FAST)  # warm-up (buffers, late-fold tables)
     if world > 1:
         same = parallel.allgather_bytes(proof, dev)
@@ -341,6 +352,8 @@ def one_large_proof(bpg, gadgets, ctx, inst, dist, local, rank, world):
     ms = barrier_max(dist, local, (time.perf_counter() - t0) * 1e3 / reps)
     if world > 1:
         parallel.disable_comm(ctx)
+    ctx.dev_free(d_w)
+    inst = host_inst
     circ.close()
     res.update({"prove_ms_fast_blinding": ms, "proofs_per_sec": 1e3 / ms,
                 "mode": "MSMs split by point range over the ranks; ncclAllGather of the partial points enqueued by libbpg on its own stream" if world > 1 else "one GPU"})
@@ -564,7 +577,9 @@ def run_ours(args):
     ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)
     ctx0.gens_ensure(GENS_CAP)
     t0 = time.perf_counter()
-    insts = gadgets.mimc_chain_instances(NBLOCKS, [5 + 1000 * rank + k for k in range(P)], ctx=ctx0)  # lane 0 of rank 0 = seed 5
+    # lane 0 of rank 0 proves the reference's own test instance (every leaf = W1, root pinned by merkle_tree_gadget.rs:476);
+    # every other lane / rank has its own random leaves
+    insts = gadgets.merkle_tree_instances(NLEAVES, [None if (rank == 0 and k == 0) else 7 + 1000 * rank + k for k in range(P)], ctx=ctx0)
     setup_s = {"instances_s": time.perf_counter() - t0}
     t0 = time.perf_counter()
     lanes = LaneSet(bpg, gadgets, local, insts, GENS_CAP, rank)
@@ -633,19 +648,35 @@ def run_ours(args):
             circ.verify(inst["label"], V0, proof0)
         extras["verify_ms"] = 1e3 * (time.perf_counter() - t0) / 3
         extras["single_warp_latency_cycles"] = ctx.bench_latency(200)
-        # MiMC (a10 / a11): independent Merkle nodes (2-block sponges), digests only and with the witness trace
-        nh = 1 << 16
-        leaves = [[os.urandom(32), os.urandom(32)] for _ in range(nh)]
-        ctx.mimc_sponge_batch(leaves[:64])
-        t0 = time.perf_counter()
-        ctx.mimc_sponge_batch(leaves)
-        dt = time.perf_counter() - t0
-        mac_per_block = 972 * 136.0
-        extras["mimc"] = {"merkle_nodes": nh, "nodes_per_sec_e2e": nh / dt, "blocks_per_sec_e2e": 2 * nh / dt,
-                          "mac32_per_sec": 2 * nh * mac_per_block / dt,
-                          "note": "host-timed through bpg_mimc_sponge_batch (upload, kernel, download); 972 mod-l multiplications = 1.32e5 MAC32 per block"}
-        if hasattr(ctx, "mimc_bench"):
-            extras["mimc"].update(ctx.mimc_bench())
+        # MiMC (a10 / a11): independent Merkle nodes (2-block sponges), digests only and with the in-circuit witness trace.
+        # Kernel time from CUDA events recorded by the library around k_mimc_sponge; 972 mod-l multiplications per block =
+        # 1.32e5 MAC32, trace mode writes 93 312 B per block.
+        mac_per_block, trace_bytes = 972 * 136.0, 972 * 96.0
+        ms_i0, mac0 = ctx.bench_imad(400)
+        peak_mac = mac0 / ms_i0 * 1e3
+        hbm_pk = 6543.1
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_pk = json.load(f).get("hbm_gbs", hbm_pk)
+        except Exception:
+            pass
+        mim = {}
+        for nh, tr in ((1 << 17, False), (1 << 13, True)):
+            leaves = [[os.urandom(32), os.urandom(32)] for _ in range(nh)]
+            ctx.mimc_sponge_batch(leaves[:256], trace=tr)
+            t0 = time.perf_counter()
+            ctx.mimc_sponge_batch(leaves, trace=tr)
+            dt = time.perf_counter() - t0
+            kms = ctx.event_elapsed_ms(14, 15)
+            blocks = 2 * nh
+            e = {"merkle_nodes": nh, "kernel_ms": kms, "blocks_per_sec_kernel": blocks / (kms * 1e-3), "nodes_per_sec_e2e": nh / dt,
+                 "mac32_per_sec": blocks * mac_per_block / (kms * 1e-3), "int_frac": blocks * mac_per_block / (kms * 1e-3) / peak_mac}
+            if tr:
+                e["hbm_write_gbs"] = blocks * trace_bytes / (kms * 1e-3) / 1e9
+                e["hbm_frac"] = e["hbm_write_gbs"] / hbm_pk
+            mim["trace" if tr else "digest"] = e
+        mim["note"] = "one thread per sponge (the rounds of one sponge are sequential); int_frac against the measured dependent fe_mul chain rate"
+        extras["mimc"] = mim
         sizes = [1 << k for k in range(16, 17 + 1)] if args.quick else [1 << k for k in range(16, 22 + 1)]
         if not args.quick:
             ctx.gens_ensure(1 << 21)
@@ -660,8 +691,8 @@ def run_ours(args):
     if world > 1 and not args.no_extras:
         extras["msm_sharded"] = msm_sharded_sweep(ctx, dist, local, rank, world, [1 << 20] if args.quick else [1 << 20, 1 << 22])
     if not args.no_extras and not args.quick:
-        # every rank must hold the SAME instance here (the lanes' witnesses differ per rank): seed 5 = rank 0's lane 0
-        shared = inst if rank == 0 else gadgets.mimc_chain_instance(NBLOCKS, seed=5, ctx=ctx0)
+        # every rank must hold the SAME instance here (the lanes' witnesses differ per rank): the reference's test instance
+        shared = inst if rank == 0 else gadgets.merkle_tree_instances(NLEAVES, [None], ctx=ctx0)[0]
         extras["one_proof_2p20"] = one_large_proof(bpg, gadgets, ctx, shared, dist, local, rank, world)
         del shared
 
@@ -675,14 +706,14 @@ def run_ours(args):
         t_gens = time.perf_counter() - t0
         t_cpu, proof_cpu, V_cpu = oracle_prove(inst, GENS_CAP, ext0, cores)
         cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": cores, "kind": "port",
-               "sample": "1 complete proof of the same 993 384-multiplier circuit on all host cores (oracle/bpo.c, OpenMP), %.1f s; "
+               "sample": "1 complete proof of the same 993 384-multiplier circuit (the reference's test instance) on all host cores (oracle/bpo.c, OpenMP), %.1f s; "
                          "BulletproofGens::new(2^20) beside it: %.1f s" % (t_cpu, t_gens),
                "proof_bytes_equal_gpu": (proof_cpu, V_cpu) == (proof0, V0)}
         if not args.quick:
             # what the reference binary does today: one thread -- on a 1/16-size circuit of the same family, scaled
-            small = gadgets.mimc_chain_instance(NBLOCKS // REF_SAMPLE_DIV, trace_on_device=False)
+            small = gadgets.merkle_tree_instances(REF_SAMPLE_LEAVES, [None], trace_on_device=False)[0]
             t_one, _, _ = oracle_prove(small, 1 << 16, ext0, 1)
-            cpu["single_thread_value"] = 1.0 / (t_one * NBLOCKS * 972 / small["n"])
+            cpu["single_thread_value"] = 1.0 / (t_one * N_MULT / small["n"])
             cpu["single_thread_sample"] = "1 thread, %d-multiplier circuit, %.1f s, scaled by the multiplier count" % (small["n"], t_one)
 
     lanes.close()  # free the 2^20 workspaces before the small-circuit extras

@@ -140,7 +140,8 @@ class Context:
             offs.append(offs[-1] + len(p))
         out = C.create_string_buffer(32 * max(n, 1))
         self.check(self.lib.bpg_mimc_hash_batch(self.h, b"".join(preimages), (C.c_uint64 * (n + 1))(*offs), n, out))
-        return [out.raw[32 * i:32 * i + 32] for i in range(n)]
+        raw = out.raw  # (.raw copies the whole buffer: take it once)
+        return [raw[32 * i:32 * i + 32] for i in range(n)]
 
     def mimc_sponge_batch(self, block_lists, trace=False):
         """block_lists: list of lists of 32-byte LE blocks -> (digests, trace bytes or None)."""
@@ -153,7 +154,8 @@ class Context:
         out = C.create_string_buffer(32 * max(n, 1))
         tr = C.create_string_buffer(offs[-1] * 972 * 96) if trace else None
         self.check(self.lib.bpg_mimc_sponge_batch(self.h, flat, (C.c_uint32 * (n + 1))(*offs), n, out, tr))
-        return [out.raw[32 * i:32 * i + 32] for i in range(n)], (tr.raw if trace else None)
+        raw = out.raw  # (.raw copies the whole buffer: take it once)
+        return [raw[32 * i:32 * i + 32] for i in range(n)], (tr.raw if trace else None)
 
     # ---- batch verification
     def verify_batch(self, items, flags=0):

@@ -31,9 +31,13 @@ extern "C" int bpg_mimc_sponge_batch(bpg_ctx *ctx, const uint8_t *blocks, const 
     uint8_t *din = (uint8_t *)ctx->scratch[6].p, *dout = (uint8_t *)ctx->scratch[7].p;
     CUDA_TRY(cudaMemcpyAsync(din, blocks, 32 * nblocks, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(din + 32 * nblocks, block_off, 4 * (n + 1), cudaMemcpyHostToDevice, s));
+    // event slots 14 / 15 bracket the kernel alone (bpg_event_elapsed_ms(ctx, 14, 15, &ms) after the call: MiMC roofline in bench.py)
+    for (int e = 14; e < 16; e++) if (!ctx->tev[e]) CUDA_TRY(cudaEventCreate(&ctx->tev[e]));
+    CUDA_TRY(cudaEventRecord(ctx->tev[14], s));
     k_mimc_sponge<<<LAUNCH_1D(n, 128), 0, s>>>((const sc *)din, (const uint32_t *)(din + 32 * nblocks), (uint32_t)n, (sc *)dout,
                                                 trace ? (sc *)(dout + 32 * n) : nullptr);
     KCHECK();
+    CUDA_TRY(cudaEventRecord(ctx->tev[15], s));
     D2H_TRY(ctx, out32, dout, 32 * n, s);
     if (trace) D2H_TRY(ctx, trace, dout + 32 * n, tbytes, s);
     SYNC_TRY(ctx, s);

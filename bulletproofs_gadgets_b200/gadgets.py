@@ -306,6 +306,95 @@ def mimc_chain_instance(nblocks, seed=5, ctx=None, label=b"mimc_chain", trace_on
     return inst
 
 
+# W1 of the reference's Merkle tests (merkle_tree_gadget.rs:126-131), big-endian as written there
+REF_W1 = bytes.fromhex("0522a64d7b931e21760cf955a15fcc793e8a52b42a56ab03afddec8beb668749")
+# root of the 512-leaf tree whose leaves are all W1 (merkle_tree_gadget.rs:476, 502)
+REF_ROOT_512 = bytes.fromhex("038c137beec8e2edfb5c48cbd063f04e569139d2221a4eb7befb85aa1bf8ba40")
+
+
+def merkle_tree_instances(nleaves, seeds, ctx=None, label=b"MerkleTree", trace_on_device=True):
+    """The reference's largest circuit: MerkleTree256 over a complete binary tree of `nleaves` committed leaves, library API
+    (test_merkle_tree_gadget_512, merkle_tree_gadget.rs:473-545: transcript "MerkleTree", 512 commitments, 511 nodes of
+    1944 multipliers = 993 384 multipliers, BulletproofGens::new(1048576, 1)).  Multipliers are laid out in the order
+    MerkleTree256::parse recurses (left subtree, right subtree, then the node's own 2-block sponge; merkle_tree_gadget.rs:75-107),
+    leaves are consumed left to right, the last constraint is  node_root - root = 0  with the root as a constant.
+    One instance per seed: seed None = the reference's test (every leaf = W1, root pinned by merkle_tree_gadget.rs:476); any
+    other seed draws random 252-bit leaves.  Node values and witness traces come from ONE batched device call per tree level
+    (all nodes of a level are independent: 256, 128, ... 1 two-block sponges per instance)."""
+    assert nleaves >= 2 and nleaves & (nleaves - 1) == 0
+    levels = nleaves.bit_length() - 1
+    csr = _Csr()
+    order = []  # (level, index in level) of every node in multiplier (post-)order
+
+    def emit(level, j):
+        """node j of `level` (level 0 = parents of the leaves) -> variable id of its digest"""
+        if level == 0:
+            left, right = [(_vid("V", 2 * j), 1)], [(_vid("V", 2 * j + 1), 1)]
+        else:
+            left = [(emit(level - 1, 2 * j), 1)]
+            right = [(emit(level - 1, 2 * j + 1), 1)]
+        mid = csr.mimc_block(left)
+        out = csr.mimc_block([(mid, 1)] + right)
+        order.append((level, j))
+        return out
+
+    top = emit(levels - 1, 0)
+    csr.rows([[(top, 1), (_vid("1", 0), 0)]])  # root constant patched per instance
+    n = csr.nmul
+    row_ptr, tv, tc = csr.finish()
+    K = len(seeds)
+    leaves, blinds = [], []
+    for sd in seeds:
+        if sd is None:
+            w1 = int.from_bytes(REF_W1, "big") & ((1 << 255) - 1)
+            leaves.append([w1] * nleaves)
+            rng = np.random.default_rng(512)
+        else:
+            rng = np.random.default_rng(sd)
+            leaves.append([int.from_bytes(rng.bytes(32), "little") & ((1 << 252) - 1) for _ in range(nleaves)])
+        blinds.append([int.from_bytes(rng.bytes(64), "little") % L_ORDER for _ in range(nleaves)])
+    # level by level: inputs of level l are the digests of level l - 1
+    cur = leaves
+    traces, width = [], nleaves // 2
+    for level in range(levels):
+        pairs = [[cur[k][2 * j], cur[k][2 * j + 1]] for k in range(K) for j in range(width)]
+        if trace_on_device:
+            ctx = ctx or Context.default()
+            digs, tr = ctx.mimc_sponge_batch([[int(a).to_bytes(32, "little"), int(b).to_bytes(32, "little")] for a, b in pairs], trace=True)
+            traces.append(np.frombuffer(tr, dtype=np.uint8).reshape(K, width, 2 * 2 * ROUNDS, 3, 32))
+            vals = [int.from_bytes(d, "little") for d in digs]
+        else:
+            rows = []
+            vals = []
+            for a, b in pairs:
+                aL, aR, aO = _mimc_trace_host([[a, b]])
+                t = np.stack([np.frombuffer(x, dtype=np.uint8).reshape(-1, 32) for x in (aL, aR, aO)], axis=1)
+                rows.append(t)
+                vals.append(int.from_bytes(aO[-32:], "little"))
+            traces.append(np.stack(rows).reshape(K, width, 2 * 2 * ROUNDS, 3, 32))
+        cur = [vals[k * width:(k + 1) * width] for k in range(K)]
+        width //= 2
+    pos = {}
+    for p_, (lv, j) in enumerate(order):
+        pos.setdefault(lv, []).append((j, p_))
+    out = []
+    for k in range(K):
+        full = np.empty((len(order), 2 * 2 * ROUNDS, 3, 32), dtype=np.uint8)
+        for lv, lst in pos.items():
+            js = np.array([j for j, _ in lst])
+            ps = np.array([p_ for _, p_ in lst])
+            full[ps] = traces[lv][k][js]
+        flat = full.reshape(n, 3, 32)
+        root = cur[k][0]
+        tck = tc if k == K - 1 else tc.copy()
+        tck[-1, :] = np.frombuffer(((-root) % L_ORDER).to_bytes(32, "little"), dtype=np.uint8)
+        out.append(dict(label=label, n=n, m=nleaves, vals=_enc(leaves[k]), blinds=_enc(blinds[k]), aL=flat[:, 0, :].tobytes(),
+                        aR=flat[:, 1, :].tobytes(), aO=flat[:, 2, :].tobytes(), csr=(row_ptr, tv, tck), root=root))
+    if seeds and seeds[0] is None and nleaves == 512:
+        assert out[0]["root"] == int.from_bytes(REF_ROOT_512, "big"), "512-leaf root differs from merkle_tree_gadget.rs:476"
+    return out
+
+
 def bounds_check_batch_instance(count, nbytes=8, seed=5, label=b"bounds_batch", lo=0, hi=None, values=None):
     """BASELINE config 3: `count` BoundsCheck gadgets (min <= v <= max on `nbytes`-byte values) in ONE proof.
     Wiring per value as in bounds_check_gadget.rs:23-49 + utils.rs:5-35: commitments (v, a = v - min, b = max - v),

@@ -186,7 +186,8 @@ int bpg_dev_free(bpg_ctx *ctx, void *d_ptr);
 int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 
-/* timing on the library's own stream: record event slot i (0..15), elapsed milliseconds between two slots */
+/* timing on the library's own stream: record event slot i (0..15), elapsed milliseconds between two slots
+ * (slots 14 / 15 are recorded by bpg_mimc_sponge_batch around its kernel) */
 int bpg_event_record(bpg_ctx *ctx, int slot);
 int bpg_event_elapsed_ms(bpg_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* per-kernel profile of the MSM bucket-accumulation kernel (the dominant kernel): while enabled every launch is

@@ -4,7 +4,7 @@ oracle prover's, byte for byte, under the same transcript label, blindings and e
   configs[1]  merkle_tree membership with mimc_hash, depth 32          n = 63 180     N = 2^16   m = 4
   configs[2]  4096 bounds_check 64-bit range gadgets, one proof        n = 524 288    N = 2^19   m = 12 288  (bit-valued witness)
   configs[3]  2^20-multiplier circuit (the reference's ignored 512-leaf test size, merkle_tree_gadget.rs:473-545)
-                                                                       n = 993 384    N = 2^20   m = 1       20 IPP rounds
+                                                                       n = 993 384    N = 2^20   m = 512     20 IPP rounds
 
 The oracle runs with all host cores (OpenMP); these three tests take about a minute on a 16-core GPU box."""
 import os
@@ -66,6 +66,9 @@ def test_config2_4096_bounds_checks_proof_bytes_equal_oracle(ctx):
 
 def test_config3_2p20_multipliers_proof_bytes_equal_oracle(ctx):
     from bulletproofs_gadgets_b200 import gadgets
-    inst = gadgets.mimc_chain_instance(1022, ctx=ctx)
-    assert inst["n"] == 993384
+    """the reference's own largest test circuit (test_merkle_tree_gadget_512, #[ignore]d there as too slow): 512 committed leaves
+    = W1, 511 MiMC nodes; the root the device computes level by level is the one pinned at merkle_tree_gadget.rs:476"""
+    inst = gadgets.merkle_tree_instances(512, [None], ctx=ctx)[0]
+    assert inst["n"] == 993384 and inst["m"] == 512
+    assert inst["root"].to_bytes(32, "big") == gadgets.REF_ROOT_512
     _check_full(ctx, inst, 1 << 20, b"\x53" * 32)
