@@ -116,8 +116,8 @@ def oracle_prove(inst, cap, ext, threads):
     """-> (seconds, proof, V) of the CPU oracle prover (oracle/bpo.c) on `threads` OpenMP threads"""
     import oracle_lib as ol
     ol.lib().bpo_set_threads(threads)
-    rp, tv, tc = inst["csr"]
-    tcb = inst.setdefault("_tc_bytes", tc.tobytes() if hasattr(tc, "tobytes") else tc)
+    rp, tv, tc = inst["csr"]  # (instances of one family share the coefficient array; reading "csr" installs this instance's constant)
+    tcb = tc.tobytes() if hasattr(tc, "tobytes") else tc
     t0 = time.perf_counter()
     proof, V = ol.r1cs_prove(inst["label"], cap, inst["aL"], inst["aR"], inst["aO"], inst["vals"], inst["blinds"], rp, tv, tcb, ext)
     return time.perf_counter() - t0, proof, V
@@ -234,16 +234,17 @@ def msm_var_sweep(ctx, sizes, reps=3, cpu_sizes=(), cores=1):
     raw[:, 31] &= 0x0F
     sc = raw.tobytes()
     for n in sizes:
-        got = ctx.msm(sc[:32 * n], pts[:32 * n])
+        sn, pn = sc[:32 * n], pts[:32 * n]  # (slicing copies: not inside the timed loop)
+        got = ctx.msm(sn, pn)
         t0 = time.perf_counter()
         for _ in range(reps):
-            ctx.msm(sc[:32 * n], pts[:32 * n])
+            ctx.msm(sn, pn)
         ms = (time.perf_counter() - t0) * 1e3 / reps
-        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3}
+        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3, "h2d_bytes": 64 * n}
         if n in cpu_sizes:
             ol.lib().bpo_set_threads(cores)
             t0 = time.perf_counter()
-            want = ol.msm(sc[:32 * n], pts[:32 * n])
+            want = ol.msm(sn, pn)
             dt = time.perf_counter() - t0
             out[str(n)].update({"cpu_mpoints_per_s": n / dt / 1e6, "cpu_cores": cores, "equals_oracle": got == want})
     return out
@@ -520,20 +521,32 @@ class LaneSet:
         self.tickets = {"next": 0, "total": 0, "lock": threading.Lock()}
         self.host_cpu_ms = 0.0
         self.region = 0
+        self.prefetch = True
 
     def _ext(self, ticket):
         # every proof of the run gets its own 32 bytes standing for the reference's thread_rng draw
         return hashlib.sha256(b"bench ext %d %d %d" % (self.rank, self.region, ticket)).digest()
 
+    def _take(self):
+        with self.tickets["lock"]:
+            if self.tickets["next"] >= self.tickets["total"]:
+                return None
+            tk = self.tickets["next"]
+            self.tickets["next"] += 1
+            return tk
+
     def _lane_run(self, ln, flags, resident):
+        """A lane works through tickets.  It always holds its NEXT ticket as well and hands that proof's opening to the library
+        (bpg_r1cs_prove_prefetch) before proving the current one, so the sequential transcript-RNG stream of proof k+1 is drawn
+        by a background host thread while proof k is on the device."""
         time.sleep(0.001 * self.lanes.index(ln))  # staggered start (inside the timed region)
-        while True:
-            with self.tickets["lock"]:
-                if self.tickets["next"] >= self.tickets["total"]:
-                    return
-                tk = self.tickets["next"]
-                self.tickets["next"] += 1
-            ln.prove(self._ext(tk), flags, resident)
+        cur = self._take()
+        while cur is not None:
+            nxt = self._take()
+            if nxt is not None and self.prefetch:
+                ln.circ.prefetch(ln.inst, self._ext(nxt), flags)
+            ln.prove(self._ext(cur), flags, resident)
+            cur = nxt
 
     def timed(self, flags, resident, steps):
         """-> (ms, launches).  The region is bracketed by a sync of every context on both sides; device time by CUDA events on
@@ -584,6 +597,12 @@ def run_ours(args):
     t0 = time.perf_counter()
     lanes = LaneSet(bpg, gadgets, local, insts, GENS_CAP, rank)
     setup_s["lanes_s"] = time.perf_counter() - t0
+    try:
+        used = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=memory.used", "--format=csv,noheader,nounits"], capture_output=True,
+                              text=True, timeout=10).stdout.strip()
+        setup_s["hbm_used_mib"] = float(used)
+    except Exception:
+        pass
     ctx, circ, inst, n = lanes.lanes[0].ctx, lanes.lanes[0].circ, insts[0], insts[0]["n"]
     RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
     FAST = bpg._lib.FLAG_FAST_BLINDING
@@ -667,12 +686,12 @@ def run_ours(args):
             t0 = time.perf_counter()
             ctx.mimc_sponge_batch(leaves, trace=tr)
             dt = time.perf_counter() - t0
-            kms = ctx.event_elapsed_ms(14, 15)
+            mk_ms = ctx.event_elapsed_ms(14, 15)
             blocks = 2 * nh
-            e = {"merkle_nodes": nh, "kernel_ms": kms, "blocks_per_sec_kernel": blocks / (kms * 1e-3), "nodes_per_sec_e2e": nh / dt,
-                 "mac32_per_sec": blocks * mac_per_block / (kms * 1e-3), "int_frac": blocks * mac_per_block / (kms * 1e-3) / peak_mac}
+            e = {"merkle_nodes": nh, "kernel_ms": mk_ms, "blocks_per_sec_kernel": blocks / (mk_ms * 1e-3), "nodes_per_sec_e2e": nh / dt,
+                 "mac32_per_sec": blocks * mac_per_block / (mk_ms * 1e-3), "int_frac": blocks * mac_per_block / (mk_ms * 1e-3) / peak_mac}
             if tr:
-                e["hbm_write_gbs"] = blocks * trace_bytes / (kms * 1e-3) / 1e9
+                e["hbm_write_gbs"] = blocks * trace_bytes / (mk_ms * 1e-3) / 1e9
                 e["hbm_frac"] = e["hbm_write_gbs"] / hbm_pk
             mim["trace" if tr else "digest"] = e
         mim["note"] = "one thread per sponge (the rounds of one sponge are sequential); int_frac against the measured dependent fe_mul chain rate"

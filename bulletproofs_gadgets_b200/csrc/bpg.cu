@@ -125,6 +125,7 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     cudaDeviceSynchronize();
     DSTEP("synced");
     if (ctx->comm) bpg_comm_destroy(ctx);
+    for (int i = 0; i < 2; i++) { prefetch_slot_free(ctx->pre[i]); ctx->pre[i] = nullptr; }
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     ctx->prof_ev.clear();
     DSTEP("prof events destroyed");
@@ -422,7 +423,7 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
     CTX_TRY(ctx->lvlP.ensure((size_t)G * (BPG_NROWS + BPG_NCOLS) * sizeof(ge)));
     CTX_TRY(ctx->lvlQ.ensure(8 * (size_t)G * sizeof(ge)));
     // large single-group MSMs: shared-memory privatised histogram / scatter (one block per SM), see kernels_msm.cuh
-    bool priv = (G == 1 && total >= BPG_PRIV_MSM_TERMS);
+    bool priv = (!vb && G <= BPG_MAX_GROUPS && total >= BPG_PRIV_MSM_TERMS);
     int sms = 0;
     if (priv) {
         // (idempotent and cheap; setting it per call keeps it correct for every device without shared mutable state)
@@ -436,9 +437,9 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
             // the 126 MB L2 and the plain cursor-ordered scatter (33 K open sectors) is faster again
             // (measured 2^19 / 2^20 / 2^21 / 2^22 terms: 1.14 / 1.90 / 3.85 / 8.11 ms privatised vs 1.18 / 1.99 / 3.60 / 6.89 ms plain)
             const bool priv_scatter = total <= (1u << 20);
-            if (scatter && priv_scatter) k_msm_scatter_smem<<<sms, 1024, BPG_NBP * 4, s>>>(P, cc, sorted);
+            if (scatter && priv_scatter) k_msm_scatter_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc, sorted);
             else if (scatter) k_msm_digits<1, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
-            else k_msm_hist_smem<<<sms, 1024, BPG_NBP * 4, s>>>(P, cc);
+            else k_msm_hist_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc);
         } else {
             if (scatter) k_msm_digits<1, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
             else k_msm_digits<0, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
@@ -540,6 +541,7 @@ extern "C" int bpg_ctx_set_shard(bpg_ctx *ctx, int rank, int world, void *d_send
     if (!ctx || world < 1 || rank < 0 || rank >= world) return BPG_E_ARG;
     if (world > 1 && (!d_send || !d_recv || !allgather || send_cap < (256u << 10))) return BPG_E_ARG;
     if (ctx->comm) bpg_comm_destroy(ctx);
+    for (int i = 0; i < 2; i++) { prefetch_slot_free(ctx->pre[i]); ctx->pre[i] = nullptr; }
     ctx->shard_rank = rank; ctx->shard_world = world;
     ctx->shard_send = d_send; ctx->shard_recv = d_recv; ctx->shard_cap = send_cap;
     ctx->shard_fn = allgather; ctx->shard_user = user;

@@ -63,6 +63,10 @@ struct gens_tables {
     ~gens_tables();
 };
 
+// bpg_r1cs_prove_prefetch (include/bpg.h): the device-free opening of one future proof, produced by a background host thread
+struct prefetch_slot;
+void prefetch_slot_free(prefetch_slot *p);
+
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -89,6 +93,7 @@ struct bpg_ctx {
     dev_buf comm_recv;        // gathered partial points of all ranks
     void *h_pinned = nullptr; size_t h_pinned_cap = 0; // two pinned staging buffers for the raw transcript-RNG draws (prover.inl)
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};      // upload of staging buffer b has completed
+    prefetch_slot *pre[2] = {nullptr, nullptr};
     cudaEvent_t tev[16] = {nullptr};
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev; // pairs (start, stop) around k_msm_accumulate

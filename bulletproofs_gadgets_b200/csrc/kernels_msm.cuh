@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
     }
 }
 
-// ---- large single-group MSMs (>= 2^19 terms): the two passes above are bound by global atomics (16 per term and pass:
+// ---- large MSMs (>= 2^19 terms, fixed-base, up to 4 output groups): the two passes above are bound by global atomics (16 per term and pass:
 // 0.61 + 1.02 ms of a 7.3 ms MSM at 2^22 terms).  Privatised versions (histogram: always; scatter: up to 2^20 terms, see msm_run): one 1024-thread block per SM keeps the 33 024
 // counters of the group in shared memory (132 KB).
 //   histogram: shared-memory atomics, then one global atomic per non-empty counter and block;
@@ -119,27 +119,39 @@ __global__ void __launch_bounds__(256) k_msm_digits(msm_params P, uint32_t *__re
 //              (cursor[b] += local count), and hands out positions inside the range with shared-memory atomics.
 // Both kernels walk the terms with the same grid-stride pattern, so a block meets the same terms in both phases.
 // The order of the pairs inside a bucket differs from the plain kernels'; the bucket sums (group elements) do not.
-__device__ __forceinline__ void msm_term_digits(const msm_params &P, uint32_t t, int *d, uint32_t &pidx) {
+// segment / group of term t without touching its scalar (the privatised kernels below skip the terms of other groups first)
+__device__ __forceinline__ const msm_seg &msm_term_seg(const msm_params &P, uint32_t t, uint32_t &j, uint32_t &grp) {
     int si = 0;
 #pragma unroll
     for (int k = 1; k < BPG_MAX_SEGS; k++)
         if (k < P.nseg && t >= P.seg[k].start) si = k;
     const msm_seg &S = P.seg[si];
-    uint32_t j = t - S.start;
+    j = t - S.start;
+    grp = S.group;
+    if (S.alt) grp ^= ((j + S.j0) >> (S.alt - 1)) & 1u;
+    return S;
+}
+__device__ __forceinline__ void msm_seg_digits(const msm_seg &S, uint32_t j, int *d, uint32_t &pidx) {
     sc k;
     ld_sc(k, &S.scalars[j]);
     if (S.reduce) sc_reduce(k, k);
     sc_digits16(d, k);
     pidx = S.p0 + j;
 }
+// grid (blocks, groups): blockIdx.y = the output group whose 33 024 counters this block keeps in shared memory; terms of other
+// groups are skipped before their scalar is read (IPP rounds: L / R alternate by halves, so a block reads half of the scalars)
 __global__ void __launch_bounds__(1024, 1) k_msm_hist_smem(msm_params P, uint32_t *__restrict__ counts) {
     extern __shared__ uint32_t scnt[];
+    const uint32_t g = blockIdx.y;
     for (uint32_t i = threadIdx.x; i < BPG_NBP; i += blockDim.x) scnt[i] = 0;
     __syncthreads();
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += gridDim.x * blockDim.x) {
+        uint32_t j, grp;
+        const msm_seg &S = msm_term_seg(P, t, j, grp);
+        if (grp != g) continue;
         int d[16];
         uint32_t pidx;
-        msm_term_digits(P, t, d, pidx);
+        msm_seg_digits(S, j, d, pidx);
 #pragma unroll
         for (int w = 0; w < 16; w++) {
             int dw = d[w];
@@ -148,19 +160,24 @@ __global__ void __launch_bounds__(1024, 1) k_msm_hist_smem(msm_params P, uint32_
         }
     }
     __syncthreads();
+    uint32_t *cg = counts + (size_t)g * BPG_NBP;
     for (uint32_t i = threadIdx.x; i < BPG_NBP; i += blockDim.x) {
         uint32_t c = scnt[i];
-        if (c) atomicAdd(&counts[i], c);
+        if (c) atomicAdd(&cg[i], c);
     }
 }
 __global__ void __launch_bounds__(1024, 1) k_msm_scatter_smem(msm_params P, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     extern __shared__ uint32_t scnt[];
+    const uint32_t g = blockIdx.y;
     for (uint32_t i = threadIdx.x; i < BPG_NBP; i += blockDim.x) scnt[i] = 0;
     __syncthreads();
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += gridDim.x * blockDim.x) {
+        uint32_t j, grp;
+        const msm_seg &S = msm_term_seg(P, t, j, grp);
+        if (grp != g) continue;
         int d[16];
         uint32_t pidx;
-        msm_term_digits(P, t, d, pidx);
+        msm_seg_digits(S, j, d, pidx);
 #pragma unroll
         for (int w = 0; w < 16; w++) {
             int dw = d[w];
@@ -169,15 +186,19 @@ __global__ void __launch_bounds__(1024, 1) k_msm_scatter_smem(msm_params P, uint
         }
     }
     __syncthreads();
+    uint32_t *cg = cursor + (size_t)g * BPG_NBP;
     for (uint32_t i = threadIdx.x; i < BPG_NBP; i += blockDim.x) { // reserve [base, base + count) of bucket i for this block
         uint32_t c = scnt[i];
-        scnt[i] = c ? atomicAdd(&cursor[i], c) : 0u;
+        scnt[i] = c ? atomicAdd(&cg[i], c) : 0u;
     }
     __syncthreads();
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += gridDim.x * blockDim.x) {
+        uint32_t j, grp;
+        const msm_seg &S = msm_term_seg(P, t, j, grp);
+        if (grp != g) continue;
         int d[16];
         uint32_t pidx;
-        msm_term_digits(P, t, d, pidx);
+        msm_seg_digits(S, j, d, pidx);
 #pragma unroll
         for (int w = 0; w < 16; w++) {
             int dw = d[w];

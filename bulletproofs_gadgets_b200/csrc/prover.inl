@@ -199,6 +199,110 @@ struct phase_trace {
     ~phase_trace() { if (on) fprintf(stderr, "[bpg prove ms]%s\n", out.c_str()); }
 };
 
+// ================================================================ prefetch of a proof's transcript-RNG stream
+// A byte-exact proof needs 2n SEQUENTIAL TranscriptRng draws (one Keccak-f each: ~0.7 s at n = 2^20, whatever the hardware) before its
+// S commitment can start; nothing else of the proof can overlap them.  A prover that knows its next job (a queue of proofs) hides
+// that latency behind the device work of the CURRENT proof: bpg_r1cs_prove_prefetch commits the openings (one small kernel),
+// then a background host thread replays the transcript opening, draws the stream through the lane-batched RNG service and stages
+// the raw draws in HBM over the context's second stream.  The matching bpg_r1cs_prove finds everything ready.
+struct prefetch_slot {
+    std::thread worker;
+    bool active = false;
+    int rc = BPG_OK;
+    // key
+    bpg_circuit *circ = nullptr;
+    std::vector<uint8_t> label, vbl;
+    uint8_t ext[32];
+    // products
+    std::vector<uint8_t> Venc;
+    bpgh::Transcript t;       // after dom-sep, V*, m
+    bpgh::Strobe rng_state;   // TranscriptRng after ib, ob, sb and the 2n bulk draws
+    sc ib, ob, sb;
+    dev_buf d_raw;            // 2n x 64 raw bytes, device
+    void *h_stage = nullptr;  // 2 pinned chunk buffers of this slot
+    cudaEvent_t ev[2] = {nullptr, nullptr}, done = nullptr;
+};
+static const size_t BPG_RNG_CHUNK = (size_t)1 << 17; // draws per staging chunk (8 MB)
+void prefetch_slot_free(prefetch_slot *p) {
+    if (!p) return;
+    if (p->worker.joinable()) p->worker.join();
+    if (p->h_stage) { explicit_bzero(p->h_stage, 2 * BPG_RNG_CHUNK * 64); cudaFreeHost(p->h_stage); }
+    if (p->d_raw.p) cudaMemset(p->d_raw.p, 0, p->d_raw.cap);
+    p->d_raw.release();
+    for (int i = 0; i < 2; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    if (p->done) cudaEventDestroy(p->done);
+    explicit_bzero(&p->rng_state, sizeof p->rng_state);
+    delete p;
+}
+static void prefetch_discard(prefetch_slot *p) { // keep the buffers, drop (and wipe) the contents
+    if (p->worker.joinable()) p->worker.join();
+    p->active = false;
+    explicit_bzero(&p->rng_state, sizeof p->rng_state);
+    explicit_bzero(&p->ib, sizeof p->ib); explicit_bzero(&p->ob, sizeof p->ob); explicit_bzero(&p->sb, sizeof p->sb);
+}
+static bool prefetch_matches(const prefetch_slot *p, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *v_blinding, const uint8_t *ext) {
+    return p && p->active && p->circ == c && p->label.size() == label_len && memcmp(p->label.data(), label, label_len) == 0 &&
+           p->vbl.size() == 32 * c->m && (c->m == 0 || memcmp(p->vbl.data(), v_blinding, 32 * c->m) == 0) && memcmp(p->ext, ext, 32) == 0;
+}
+extern "C" int bpg_r1cs_prove_prefetch(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *v, const uint8_t *v_blinding,
+                                       const uint8_t ext_rng32[32], unsigned flags) {
+    if (!ctx || !c || !label || !ext_rng32 || (c->m && (!v || !v_blinding))) return BPG_E_ARG;
+    if (flags & BPG_FLAG_FAST_BLINDING) return BPG_OK; // nothing sequential to hide
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int si = -1;
+    for (int i = 0; i < 2; i++) if (!ctx->pre[i] || !ctx->pre[i]->active) { si = i; break; }
+    if (si < 0) return BPG_OK; // both slots hold pending proofs: the hint is dropped, the proof will draw its stream itself
+    if (!ctx->pre[si]) ctx->pre[si] = new prefetch_slot();
+    prefetch_slot *p = ctx->pre[si];
+    if (p->worker.joinable()) p->worker.join();
+    size_t n = c->n, m = c->m;
+    if (!p->h_stage) {
+        CUDA_TRY(cudaHostAlloc(&p->h_stage, 2 * BPG_RNG_CHUNK * 64, cudaHostAllocDefault));
+        for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    }
+    CTX_TRY(p->d_raw.ensure(128 * n + 64));
+    p->circ = c; p->label.assign(label, label + label_len); p->vbl.assign(v_blinding, v_blinding + 32 * m); memcpy(p->ext, ext_rng32, 32);
+    p->Venc.assign(32 * (m ? m : 1), 0);
+    if (m) CTX_TRY(bpg_pedersen_commit(ctx, v, v_blinding, m, p->Venc.data())); // the only device work of the opening (this thread, main stream)
+    else SYNC_TRY(ctx, ctx->stream); // (the commit call synchronises too: nothing of an earlier proof still touches this slot's buffers)
+    p->rc = BPG_OK;
+    p->active = true;
+    int device = ctx->device;
+    cudaStream_t s2 = ctx->stream2;
+    p->worker = std::thread([p, n, m, device, s2] {
+        cudaSetDevice(device);
+        bpgh::Transcript t(p->label.data(), p->label.size());
+        t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
+        for (size_t i = 0; i < m; i++) t.append("V", p->Venc.data() + 32 * i, 32);
+        t.append_u64("m", m);
+        p->t = t;
+        bpgh::TranscriptRng rng(t);
+        for (size_t i = 0; i < m; i++) rng.rekey_with_witness_bytes("v_blinding", p->vbl.data() + 32 * i, 32);
+        rng.finalize(p->ext);
+        p->ib = rng_scalar(rng); p->ob = rng_scalar(rng); p->sb = rng_scalar(rng);
+        size_t total = 2 * n, done = 0;
+        int used[2] = {0, 0};
+        for (size_t ck = 0; done < total; ck++) {
+            int b = (int)(ck & 1);
+            size_t cnt = std::min(BPG_RNG_CHUNK, total - done);
+            uint8_t *hb = (uint8_t *)p->h_stage + (size_t)b * BPG_RNG_CHUNK * 64;
+            if (used[b] && cudaEventSynchronize(p->ev[b]) != cudaSuccess) { p->rc = BPG_E_CUDA; break; }
+            bpgh::RngService::get().draw64(rng, hb, cnt);
+            if (cudaMemcpyAsync((uint8_t *)p->d_raw.p + 64 * done, hb, 64 * cnt, cudaMemcpyHostToDevice, s2) != cudaSuccess ||
+                cudaEventRecord(p->ev[b], s2) != cudaSuccess) { p->rc = BPG_E_CUDA; break; }
+            used[b] = 1;
+            done += cnt;
+        }
+        if (cudaEventRecord(p->done, s2) != cudaSuccess) p->rc = BPG_E_CUDA;
+        if (cudaEventSynchronize(p->done) != cudaSuccess) p->rc = BPG_E_CUDA; // uploads complete: the staging buffers can be wiped
+        explicit_bzero(p->h_stage, 2 * BPG_RNG_CHUNK * 64);
+        p->rng_state = rng.s;
+        explicit_bzero(&rng, sizeof rng);
+    });
+    return BPG_OK;
+}
+
 // ================================================================ Prover::prove
 // Buffer map (ctx->scratch):  8: witness aL|aR|aO|sL|sR (5N)   9: small scalars   10: power tables   11: w (3n+m+1)
 //                            12: l1|r0|r1|r3 (4n) -> later sG|sH (2N)   13: a|b|EG|EH (4N)   14: partial sums   15: flatten partials
@@ -222,18 +326,36 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
 
     const int shard_on = ctx->shard_world > 1; // one proof over several ranks: MSMs cut by point range (bpg_ctx_set_shard)
     phase_trace tr;
+    // a prefetched opening for exactly this proof (bpg_r1cs_prove_prefetch)?  Anything else that is pending stays for its own proof.
+    prefetch_slot *pre = nullptr;
+    if (!(flags & BPG_FLAG_FAST_BLINDING))
+        for (int i = 0; i < 2 && !pre; i++)
+            if (prefetch_matches(ctx->pre[i], c, label, label_len, v_blinding, ext_rng32)) pre = ctx->pre[i];
+    if (pre) {
+        if (pre->worker.joinable()) pre->worker.join();
+        if (pre->rc != BPG_OK) { prefetch_discard(pre); pre = nullptr; }
+    }
     bpgh::Transcript t(label, label_len);
-    t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
-    // ---- V_i = v_i B + blinding_i B~  (batched; Prover::commit appends each to the transcript)
     std::vector<uint8_t> Venc(32 * (m ? m : 1));
-    if (m) CTX_TRY(bpg_pedersen_commit(ctx, v, v_blinding, m, Venc.data()));
-    for (size_t i = 0; i < m; i++) t.append("V", Venc.data() + 32 * i, 32);
-    if (V_out && m) memcpy(V_out, Venc.data(), 32 * m);
-    t.append_u64("m", m);
     bpgh::TranscriptRng rng(t);
-    for (size_t i = 0; i < m; i++) rng.rekey_with_witness_bytes("v_blinding", v_blinding + 32 * i, 32);
-    rng.finalize(ext_rng32);
-    sc ib = rng_scalar(rng), ob = rng_scalar(rng), sb = rng_scalar(rng);
+    sc ib, ob, sb;
+    if (pre) {
+        t = pre->t;
+        Venc = pre->Venc;
+        rng.s = pre->rng_state;
+        ib = pre->ib; ob = pre->ob; sb = pre->sb;
+    } else {
+        t.append("dom-sep", (const uint8_t *)"r1cs v1", 7);
+        // ---- V_i = v_i B + blinding_i B~  (batched; Prover::commit appends each to the transcript)
+        if (m) CTX_TRY(bpg_pedersen_commit(ctx, v, v_blinding, m, Venc.data()));
+        for (size_t i = 0; i < m; i++) t.append("V", Venc.data() + 32 * i, 32);
+        t.append_u64("m", m);
+        rng = bpgh::TranscriptRng(t);
+        for (size_t i = 0; i < m; i++) rng.rekey_with_witness_bytes("v_blinding", v_blinding + 32 * i, 32);
+        rng.finalize(ext_rng32);
+        ib = rng_scalar(rng); ob = rng_scalar(rng); sb = rng_scalar(rng);
+    }
+    if (V_out && m) memcpy(V_out, Venc.data(), 32 * m);
     tr.mark("commitV");
 
     // ---- upload the witness, start A_I1 / A_O1 while the host draws s_L, s_R
@@ -285,8 +407,16 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         // other provers of this process); Scalar::from_bytes_mod_order_wide happens on the device.  The stream is drawn in
         // chunks into two pinned staging buffers and each chunk is uploaded while the next one is drawn: no pageable-memory
         // staging copy by the driver (measured at n = 2^20: 128 MB per proof), and only 2 x 8 MB of secrets to wipe.
-        if (n) {
-            const size_t CHUNK = (size_t)1 << 17; // draws per chunk (8 MB)
+        if (n && pre) {
+            // the stream was drawn and staged in HBM while the previous proof was on the device
+            CUDA_TRY(cudaStreamWaitEvent(s, pre->done, 0));
+            tr.mark("rng(prefetched)");
+            k_sc_reduce_wide<<<LAUNCH_1D(2 * n, 128), 0, s>>>((const uint32_t *)pre->d_raw.p, (uint32_t)n, d_sL, d_sR);
+            KCHECK();
+            CUDA_TRY(cudaMemsetAsync(pre->d_raw.p, 0, 128 * n, s));
+            prefetch_discard(pre);
+        } else if (n) {
+            const size_t CHUNK = BPG_RNG_CHUNK; // draws per chunk (8 MB)
             if (!ctx->h_pinned) {
                 CUDA_TRY(cudaHostAlloc(&ctx->h_pinned, 2 * CHUNK * 64, cudaHostAllocDefault));
                 ctx->h_pinned_cap = 2 * CHUNK * 64;

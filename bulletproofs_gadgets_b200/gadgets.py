@@ -236,6 +236,18 @@ def merkle_path_instance(depth, leaf=b"\x43", seed=4, ctx=None, label=b"merkle_p
     return dict(label=label, n=n, m=4, vals=_enc(vals), blinds=_enc(blinds), aL=aL, aR=aR, aO=aO, csr=csr.finish(), root=cur_val)
 
 
+class _Instance(dict):
+    """Instance dict whose CSR coefficient array is SHARED with the other instances of the same circuit family (160 MB at 2^20
+    multipliers): the only per-instance coefficient is the last one (digest / root constant), kept in "last_coeff" and written
+    into the shared array whenever this instance's "csr" is read.  Single-threaded use of "csr" is assumed."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if key == "csr" and "last_coeff" in self:
+            v[2][-1, :] = np.frombuffer(dict.__getitem__(self, "last_coeff"), dtype=np.uint8)
+        return v
+
+
 def _mimc_trace_host(sponges):
     """(a_L, a_R, a_O) bytes of the MiMC chains in gadget order, host big-int (front-end / CPU-only callers)"""
     aL, aR, aO = [], [], []
@@ -288,11 +300,9 @@ def mimc_chain_instances(nblocks, seeds, ctx=None, label=b"mimc_chain", trace_on
         dvals = [int.from_bytes(tr[2][-32:], "little") for tr in traces]
     out = []
     for k in range(len(seeds)):
-        tck = tc if k == len(seeds) - 1 else tc.copy()  # the last instance may keep the shared array
-        tck[-1, :] = np.frombuffer(((-dvals[k]) % L_ORDER).to_bytes(32, "little"), dtype=np.uint8)
         aL, aR, aO = traces[k]
-        out.append(dict(label=label, n=n, m=1, vals=_enc([firsts[k]]), blinds=_enc([blinds[k]]), aL=aL, aR=aR, aO=aO,
-                        csr=(row_ptr, tv, tck), root=dvals[k]))
+        out.append(_Instance(label=label, n=n, m=1, vals=_enc([firsts[k]]), blinds=_enc([blinds[k]]), aL=aL, aR=aR, aO=aO,
+                             csr=(row_ptr, tv, tc), root=dvals[k], last_coeff=((-dvals[k]) % L_ORDER).to_bytes(32, "little")))
     return out
 
 
@@ -386,10 +396,9 @@ def merkle_tree_instances(nleaves, seeds, ctx=None, label=b"MerkleTree", trace_o
             full[ps] = traces[lv][k][js]
         flat = full.reshape(n, 3, 32)
         root = cur[k][0]
-        tck = tc if k == K - 1 else tc.copy()
-        tck[-1, :] = np.frombuffer(((-root) % L_ORDER).to_bytes(32, "little"), dtype=np.uint8)
-        out.append(dict(label=label, n=n, m=nleaves, vals=_enc(leaves[k]), blinds=_enc(blinds[k]), aL=flat[:, 0, :].tobytes(),
-                        aR=flat[:, 1, :].tobytes(), aO=flat[:, 2, :].tobytes(), csr=(row_ptr, tv, tck), root=root))
+        out.append(_Instance(label=label, n=n, m=nleaves, vals=_enc(leaves[k]), blinds=_enc(blinds[k]), aL=flat[:, 0, :].tobytes(),
+                             aR=flat[:, 1, :].tobytes(), aO=flat[:, 2, :].tobytes(), csr=(row_ptr, tv, tc), root=root,
+                             last_coeff=((-root) % L_ORDER).to_bytes(32, "little")))
     if seeds and seeds[0] is None and nleaves == 512:
         assert out[0]["root"] == int.from_bytes(REF_ROOT_512, "big"), "512-leaf root differs from merkle_tree_gadget.rs:476"
     return out
@@ -461,7 +470,11 @@ class Circuit:
         row_ptr, tv, tc = csr
         row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
         tv = np.ascontiguousarray(tv, dtype=np.uint32)
-        tcb = tc if isinstance(tc, (bytes, bytearray)) else np.ascontiguousarray(tc, dtype=np.uint8).tobytes()
+        if isinstance(tc, (bytes, bytearray)):
+            tcb = bytes(tc)
+        else:
+            tc = np.ascontiguousarray(tc, dtype=np.uint8)
+            tcb = C.cast(tc.ctypes.data, C.c_char_p)  # no copy: the library reads it during the call only
         self.ctx, self.n, self.m = ctx, n, m
         h = C.c_void_p()
         ctx.check(ctx.lib.bpg_circuit_create(ctx.h, n, m, len(row_ptr) - 1, row_ptr.ctypes.data_as(C.POINTER(C.c_uint32)),
@@ -477,6 +490,10 @@ class Circuit:
         if rc < 0:
             self.ctx.check(rc)
         return proof.raw[:rc], V.raw[:32 * self.m]
+
+    def prefetch(self, inst, ext_rng32, flags=0):
+        """start the transcript-RNG stream of a FUTURE prove(inst, ext_rng32) in the background (bpg_r1cs_prove_prefetch)"""
+        self.ctx.check(self.ctx.lib.bpg_r1cs_prove_prefetch(self.ctx.h, self.h, inst["label"], len(inst["label"]), inst["vals"], inst["blinds"], ext_rng32, flags))
 
     def verify(self, label, V, proof, ext_rng32=None, flags=0):
         """ext_rng32 stands for the verifier's thread_rng draw: fresh secret randomness unless a test pins it"""

@@ -149,6 +149,15 @@ void bpg_circuit_destroy(bpg_circuit *c);
 long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *aL,
                     const uint8_t *aR, const uint8_t *aO, const uint8_t *v, const uint8_t *v_blinding,
                     const uint8_t ext_rng32[32], unsigned flags, uint8_t *V_out, uint8_t *proof, size_t proof_cap);
+/* Pipelining hint for a prover that knows its NEXT proof (a queue of jobs).  The 2n transcript-RNG draws behind s_L, s_R are
+ * sequential (one Keccak-f each, ~0.7 s of one host core at n = 2^20) and nothing of a proof can overlap its own draws; this call
+ * starts them for a FUTURE proof in the background -- it commits the openings (one small kernel), then a host thread draws the
+ * stream through the lane-batched RNG service and stages it in HBM on the context's second stream -- and returns at once, so
+ * the draws of proof k+1 hide behind the device work of proof k on the same context.  The next bpg_r1cs_prove on this context
+ * whose (circuit, label, v_blinding, ext_rng32) are the same picks the stream up; proof bytes are identical with or without
+ * the hint.  Up to two proofs can be pending; further hints are ignored.  flags as for bpg_r1cs_prove. */
+int bpg_r1cs_prove_prefetch(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *v,
+                            const uint8_t *v_blinding, const uint8_t ext_rng32[32], unsigned flags);
 /* Verifier::new(label) + commit(V_i)* + (constraints) + verify(&proof,&pc_gens,&bp_gens)  [ext; verifier.rs:51-53,90].
  * *accept = 1 for Ok(()), 0 for Err(VerificationError | FormatError); the return value only reports library errors. */
 int bpg_r1cs_verify(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *label, size_t label_len, const uint8_t *V32,

@@ -223,3 +223,38 @@ def test_concurrent_provers_match_oracle():
     for c in ctxs:
         c.close()
     assert len(out) == 24 and all(v == (want, Vw) for v in out.values())
+
+
+def test_prefetched_opening_gives_identical_proofs(ctx):
+    """bpg_r1cs_prove_prefetch: the transcript-RNG stream of a future proof drawn in the background.  Proof bytes must equal the
+    oracle's whether the hint was given, given for another proof (ignored / kept pending), or given for two proofs at once."""
+    import circuits
+    inst = circuits.chain_instance(300, 77)
+    import ctypes as C
+    rp, tv, tc = inst["csr"]
+    h = C.c_void_p()
+    ctx.check(ctx.lib.bpg_circuit_create(ctx.h, inst["n"], 3, len(rp) - 1, (C.c_uint32 * len(rp))(*rp), (C.c_uint32 * max(1, len(tv)))(*tv), tc, C.byref(h)))
+
+    def prove(ext):
+        cap = 1 + 32 * (14 + 64 + 2)
+        proof, V = C.create_string_buffer(cap), C.create_string_buffer(96)
+        rc = ctx.lib.bpg_r1cs_prove(ctx.h, h, inst["label"], len(inst["label"]), inst["aL"], inst["aR"], inst["aO"], inst["vals"], inst["blinds"], ext, 0, V, proof, cap)
+        assert rc > 0
+        return proof.raw[:rc], V.raw
+
+    def prefetch(ext, blinds=None):
+        ctx.check(ctx.lib.bpg_r1cs_prove_prefetch(ctx.h, h, inst["label"], len(inst["label"]), inst["vals"], blinds or inst["blinds"], ext, 0))
+
+    exts = [bytes([k]) * 32 for k in range(1, 6)]
+    want = [oracle_prove(inst, 4096, e) for e in exts]
+    assert prove(exts[0]) == want[0]                      # no hint
+    prefetch(exts[1])
+    assert prove(exts[1]) == want[1]                      # hinted
+    prefetch(exts[2]); prefetch(exts[3])                  # two pending
+    prefetch(exts[4])                                     # third hint: dropped
+    assert prove(exts[3]) == want[3]                      # consumed out of order
+    assert prove(exts[4]) == want[4]                      # never prefetched
+    assert prove(exts[2]) == want[2]                      # still pending from before
+    prefetch(exts[0], blinds=inst["blinds"][32:] + inst["blinds"][:32])  # hint for other blindings: must not be used
+    assert prove(exts[0]) == want[0]
+    ctx.lib.bpg_circuit_destroy(h)
