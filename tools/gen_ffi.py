@@ -21,9 +21,9 @@ def param(p):
     const = "const" in ty
     base = ty.replace("const", "").replace("*", "").strip()
     stars = ty.count("*") + (1 if arr else 0)
-    if stars == 2 and base == "bpg_circuit":
+    if stars == 2 and const and base == "bpg_circuit":   # bpg_circuit *const *circuits
         return name, "*const *mut BpgCircuit"
-    if stars == 2 and base == "uint8_t":
+    if stars == 2 and const and base == "uint8_t":       # const uint8_t *const *labels
         return name, "*const *const u8"
     rt = BASE[base]
     for i in range(stars):
