@@ -383,7 +383,9 @@ def _cfg5_assemble(job):
     p = run.prover
     enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
     rp, tv, tc = p.csr()
-    return (k, label, p.num_vars, len(p.v), rp, tv, tc, enc(p.aL), enc(p.aR), enc(p.aO), enc(p.v), enc(p.v_blinding), valid)
+    # the assignment is evaluated on the proving context's device (bpg_witness_eval): hand over the recorded combinations
+    wit = (enc(p._in_L), enc(p._in_R), list(p._w_ptr), list(p._w_var), bytes(p._w_coeff))
+    return (k, label, p.num_vars, len(p.v), rp, tv, tc, wit, enc(p.v), enc(p.v_blinding), valid)
 
 
 def batch_verify_config5(bpg, ctx, dist, local, rank, world, total, cores):
@@ -414,7 +416,9 @@ def batch_verify_config5(bpg, ctx, dist, local, rank, world, total, cores):
     def prove_slice(ci):
         c = ctxs[ci]
         for idx in range(ci, len(built), nctx):
-            k, label, n, m, rp, tv, tc, aL, aR, aO, v, vb, valid = built[idx]
+            k, label, n, m, rp, tv, tc, (inL, inR, wp, wv, wc), v, vb, valid = built[idx]
+            aL, aR, aO = C.create_string_buffer(inL, 32 * n), C.create_string_buffer(inR, 32 * n), C.create_string_buffer(32 * n)
+            c.check(c.lib.bpg_witness_eval(c.h, n, m, (C.c_uint32 * len(wp))(*wp), (C.c_uint32 * max(1, len(wv)))(*wv), wc, v, aL, aR, aO))
             h = C.c_void_p()
             c.check(c.lib.bpg_circuit_create(c.h, n, m, len(rp) - 1, (C.c_uint32 * len(rp))(*rp), (C.c_uint32 * max(1, len(tv)))(*tv), tc, C.byref(h)))
             cap = 1 + 32 * (14 + 64 + 2)

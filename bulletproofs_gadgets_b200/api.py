@@ -311,7 +311,11 @@ class _ConstraintSystem:
         self.label = bytes(label)
         self.is_prover = prover
         self.row_ptr, self.term_var, self.term_coeff = [0], [], bytearray()
-        self.aL, self.aR, self.aO = [], [], []
+        # prover side: caller-assigned a_L, a_R (allocate / allocate_multiplier) and, for multiply(), the pair of linear
+        # combinations per multiplier; the assignment itself is computed on the device at prove() (bpg_witness_eval)
+        self._in_L, self._in_R = [], []
+        self._w_ptr, self._w_var, self._w_coeff = [0], [], bytearray()
+        self._witness = None
         self.v, self.v_blinding, self.V = [], [], []
         self.num_vars = 0
         self._pending = None
@@ -326,13 +330,32 @@ class _ConstraintSystem:
         """(row_ptr, term_var, term_coeff bytes) of the recorded constraints"""
         return list(self.row_ptr), list(self.term_var), bytes(self.term_coeff)
 
-    # -- evaluation of linear combinations over the prover's assignment (Prover::eval)
-    def _eval(self, lc):
-        acc = 0
+    # -- the prover's assignment (Prover::eval of every multiply(), cs_buffer.rs:94-97 / prover.rs:102-117) is evaluated on
+    # the device, level by level of the dependency graph, in ONE call when it is first needed
+    def _push_witness_lc(self, lc):
         for (k, i), c in lc:
-            val = 1 if k == "1" else {"L": self.aL, "R": self.aR, "O": self.aO, "V": self.v}[k][i]
-            acc += val * c
-        return acc % L_ORDER
+            self._w_var.append((_KIND[k] << 29) | i)
+            self._w_coeff += int(c % L_ORDER).to_bytes(32, "little")
+        self._w_ptr.append(len(self._w_var))
+
+    def witness_bytes(self):
+        """(a_L, a_R, a_O) as n x 32-byte LE strings, computed by bpg_witness_eval (cached until the system grows)"""
+        n, m = self.num_vars, len(self.v)
+        if self._witness is not None and self._witness[0] == (n, m):
+            return self._witness[1]
+        enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
+        aL, aR = C.create_string_buffer(enc(self._in_L), 32 * max(1, n)), C.create_string_buffer(enc(self._in_R), 32 * max(1, n))
+        aO = C.create_string_buffer(32 * max(1, n))
+        ptr = (C.c_uint32 * (2 * n + 1))(*self._w_ptr)
+        tv = (C.c_uint32 * max(1, len(self._w_var)))(*self._w_var)
+        self.ctx.check(self.ctx.lib.bpg_witness_eval(self.ctx.h, n, m, ptr, tv, bytes(self._w_coeff), enc(self.v), aL, aR, aO))
+        self._witness = ((n, m), (aL.raw[:32 * n], aR.raw[:32 * n], aO.raw[:32 * n]))
+        return self._witness[1]
+
+    def witness(self):
+        """(a_L, a_R, a_O) as lists of integers"""
+        dec = lambda b: [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(len(b) // 32)]
+        return tuple(dec(b) for b in self.witness_bytes())
 
     def _push_row(self, lc):
         for (k, i), c in lc:
@@ -344,8 +367,8 @@ class _ConstraintSystem:
         i = self.num_vars
         self.num_vars += 1
         if self.is_prover:
-            l, r = self._eval(left), self._eval(right)
-            self.aL.append(l); self.aR.append(r); self.aO.append(l * r % L_ORDER)
+            self._in_L.append(0); self._in_R.append(0)
+            self._push_witness_lc(left); self._push_witness_lc(right)
         self._push_row(list(left) + [(("L", i), L_ORDER - 1)])
         self._push_row(list(right) + [(("R", i), L_ORDER - 1)])
         return ("L", i), ("R", i), ("O", i)
@@ -357,7 +380,8 @@ class _ConstraintSystem:
         self.num_vars += 1
         if self.is_prover:
             l, r = input_assignments
-            self.aL.append(l % L_ORDER); self.aR.append(r % L_ORDER); self.aO.append(l * r % L_ORDER)
+            self._in_L.append(l % L_ORDER); self._in_R.append(r % L_ORDER)
+            self._w_ptr += [len(self._w_var)] * 2
         return ("L", i), ("R", i), ("O", i)
 
     def allocate(self, assignment=None):
@@ -368,12 +392,12 @@ class _ConstraintSystem:
             self.num_vars += 1
             self._pending = i
             if self.is_prover:
-                self.aL.append(assignment % L_ORDER); self.aR.append(0); self.aO.append(0)
+                self._in_L.append(assignment % L_ORDER); self._in_R.append(0)
+                self._w_ptr += [len(self._w_var)] * 2
             return ("L", i)
         i, self._pending = self._pending, None
         if self.is_prover:
-            self.aR[i] = assignment % L_ORDER
-            self.aO[i] = self.aL[i] * self.aR[i] % L_ORDER
+            self._in_R[i] = assignment % L_ORDER
         return ("R", i)
 
     def constrain(self, lc):
@@ -430,7 +454,8 @@ class Prover(_ConstraintSystem):
             enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
             cap = 1 + 32 * (14 + 64 + 2)
             proof, V = C.create_string_buffer(cap), C.create_string_buffer(32 * max(1, m))
-            rc = self.ctx.lib.bpg_r1cs_prove(self.ctx.h, circ, self.label, len(self.label), enc(self.aL), enc(self.aR), enc(self.aO),
+            aL, aR, aO = self.witness_bytes()
+            rc = self.ctx.lib.bpg_r1cs_prove(self.ctx.h, circ, self.label, len(self.label), aL, aR, aO,
                                              enc(self.v), enc(self.v_blinding), ext, flags, V, proof, cap)
             if rc < 0:
                 self.ctx.check(rc)

@@ -611,12 +611,12 @@ int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t npri
     CTX_TRY(ctx->mat_tab.ensure((size_t)BPG_NWIN * pt_small * sizeof(ge_an)));
     uint32_t cap = (uint32_t)ctx->cap, ptotal = ctx->ptotal;
     const bool sharded = shard && ctx->shard_world > 1;
-    uint32_t t0 = 0, t1 = 2 * N; // this rank's slice of the 2N input terms
-    if (sharded) shard_slice(2 * N, ctx->shard_rank, ctx->shard_world, t0, t1);
-    uint32_t nt = t1 - t0;
+    uint32_t p0 = 0, p1 = N; // this rank's point range of BOTH vectors (the per-segment slices of the round MSMs)
+    if (sharded) shard_slice(N, ctx->shard_rank, ctx->shard_world, p0, p1);
+    uint32_t nt = 2 * (p1 - p0);
     CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)nt * BPG_NWIN * 2, nt != 0, ctx->tab, lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
-        if (scatter) k_mat_digits<1><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, t0, t1, cc, sorted);
-        else k_mat_digits<0><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, t0, t1, cc, sorted);
+        if (scatter) k_mat_digits<1><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, p0, p1, cc, sorted);
+        else k_mat_digits<0><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, p0, p1, cc, sorted);
     }));
     k_mat_reduce<<<nout, 32, 0, s>>>((const ge *)ctx->buckets.p, nout, (ge *)ctx->mat_pts.p);
     KCHECK();

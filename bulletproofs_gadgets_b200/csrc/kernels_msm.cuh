@@ -529,13 +529,16 @@ __global__ void __launch_bounds__(32) k_msm_combine(const ge *__restrict__ in8, 
 // output, no extra tables, no doublings).  Output = sum_b b * low_b + 256 * sum_b b * high_b.
 // The sort / accumulate / finish kernels above are reused unchanged (bucket = (2 * output + set) * 129 + |digit|).
 #define BPG_MAT_NB 129u
+// [p0, p1): this rank's point range (all of [0, N) unless the proof is sharded): thread t < p1 - p0 handles G_{p0 + t}, the next
+// p1 - p0 threads handle H_{p0 + ..} -- the same per-vector slices the round MSMs use, so EG / EH are only ever needed there
 template <int SCATTER>
 __global__ void __launch_bounds__(256) k_mat_digits(uint32_t N, uint32_t nprime, uint32_t cap, uint32_t ptotal, const sc *__restrict__ EG, const sc *__restrict__ EH,
-                                                     uint32_t t0, uint32_t t1, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
-    uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x; // [t0, t1): this rank's slice of the 2N terms (all of them unless sharded)
-    if (t >= t1) return;
-    bool isH = t >= N;
-    uint32_t p = isH ? t - N : t;
+                                                     uint32_t p0, uint32_t p1, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, span = p1 - p0;
+    if (t >= 2 * span) return;
+    bool isH = t >= span;
+    uint32_t p = p0 + (isH ? t - span : t);
+    (void)N;
     sc k;
     ld_sc(k, isH ? &EH[p] : &EG[p]);
     int d[16];

@@ -258,10 +258,11 @@ __global__ void k_ipp_cw(const sc *__restrict__ c2, const sc *__restrict__ w, sc
 // Scalars of the round's two MSMs over the ORIGINAL generators (no folded generators are materialised):
 // with r = i mod nj:  r >= h:  G_i -> L with a[r-h]*EG[i],  H_i -> R with b[r-h]*EH[i]
 //                     r <  h:  G_i -> R with a[h+r]*EG[i],  H_i -> L with b[h+r]*EH[i]
+// [i0, i1): the part of [0, N) this call has to produce (a rank of a sharded proof only needs the scalars of its own point range)
 __global__ void __launch_bounds__(128) k_ipp_expand(uint32_t N, uint32_t nj, const sc *__restrict__ a, const sc *__restrict__ b, const sc *__restrict__ EG,
-                                                     const sc *__restrict__ EH, sc *__restrict__ sG, sc *__restrict__ sH) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+                                                     const sc *__restrict__ EH, sc *__restrict__ sG, sc *__restrict__ sH, uint32_t i0, uint32_t i1) {
+    uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1 || i >= N) return;
     uint32_t h = nj >> 1, r = i & (nj - 1);
     uint32_t src = r >= h ? r - h : r + h;
     sc av, bv, eg, eh, p;
@@ -270,18 +271,20 @@ __global__ void __launch_bounds__(128) k_ipp_expand(uint32_t N, uint32_t nj, con
     sc_mul(p, bv, eh); st_sc(&sH[i], p);
 }
 // a' = a_lo u + a_hi u^-1 ; b' = b_lo u^-1 + b_hi u ; EG[i] *= (right half ? u : u^-1) ; EH[i] *= (right half ? u^-1 : u)
-// uu = [u, u^-1]
+// uu = [u, u^-1].  The per-generator factors are only updated on [i0, i1) (see k_ipp_expand); a, b always in full.
 __global__ void __launch_bounds__(128) k_ipp_fold(uint32_t N, uint32_t nj, const sc *__restrict__ uu, sc *__restrict__ a, sc *__restrict__ b, sc *__restrict__ EG,
-                                                   sc *__restrict__ EH) {
+                                                   sc *__restrict__ EH, uint32_t i0, uint32_t i1) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t h = nj >> 1;
     sc u, ui;
     ld_sc(u, &uu[0]); ld_sc(ui, &uu[1]);
-    bool right = (i & (nj - 1)) >= h;
     sc e, p;
-    ld_sc(e, &EG[i]); sc_mul(p, e, right ? u : ui); st_sc(&EG[i], p);
-    ld_sc(e, &EH[i]); sc_mul(p, e, right ? ui : u); st_sc(&EH[i], p);
+    if (i >= i0 && i < i1) {
+        bool right = (i & (nj - 1)) >= h;
+        ld_sc(e, &EG[i]); sc_mul(p, e, right ? u : ui); st_sc(&EG[i], p);
+        ld_sc(e, &EH[i]); sc_mul(p, e, right ? ui : u); st_sc(&EH[i], p);
+    }
     if (i < h) {
         sc lo, hi, q;
         ld_sc(lo, &a[i]); ld_sc(hi, &a[h + i]);
@@ -345,6 +348,49 @@ __global__ void __launch_bounds__(128) k_verify_scalars(uint32_t n, uint32_t N, 
     }
     block_sum_scalars<1>(&d, smem);
     if (threadIdx.x == 0) st_sc(&dparts[blockIdx.x], d);
+}
+
+// ---------------------------------------------------------------- witness evaluation
+// ConstraintSystem::multiply(left, right) of the reference evaluates both linear combinations over the assignment so far
+// (cs_buffer.rs:94-97 -> Prover::multiply, replayed by prover.rs:102-117): a_L[i] = <left_i>, a_R[i] = <right_i>, a_O[i] = a_L a_R.
+// One thread per multiplier of the current dependency level (order[k0 .. k1)): every variable an LC references is either a
+// committed value, One, or a multiplier of an earlier level.  var = kind << 29 | index (kind 0 a_L, 1 a_R, 2 a_O, 3 V, 4 One).
+__device__ __forceinline__ void lc_eval(sc &acc, uint32_t t0, uint32_t t1, const uint32_t *__restrict__ term_var, const sc *__restrict__ term_coeff,
+                                        const sc *aL, const sc *aR, const sc *aO, const sc *__restrict__ v) {
+    sc_zero(acc);
+#pragma unroll 1
+    for (uint32_t t = t0; t < t1; t++) {
+        uint32_t var = term_var[t], kind = var >> 29, idx = var & 0x1FFFFFFFu;
+        sc cf, val, p;
+        ld_sc(cf, &term_coeff[t]);
+        if (kind == 4) { sc_add_r(acc, acc, cf); continue; }
+        ld_sc(val, kind == 0 ? &aL[idx] : kind == 1 ? &aR[idx] : kind == 2 ? &aO[idx] : &v[idx]);
+        sc_mul(p, cf, val);
+        sc_add_r(acc, acc, p);
+    }
+}
+__global__ void __launch_bounds__(128) k_witness_level(const uint32_t *__restrict__ order, uint32_t k0, uint32_t k1, const uint32_t *__restrict__ lc_ptr,
+                                                        const uint32_t *__restrict__ term_var, const sc *__restrict__ term_coeff, sc *aL, sc *aR, sc *aO,
+                                                        const sc *__restrict__ v) {
+    uint32_t k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    uint32_t i = order[k];
+    sc l, r, o;
+    lc_eval(l, lc_ptr[2 * i], lc_ptr[2 * i + 1], term_var, term_coeff, aL, aR, aO, v);
+    lc_eval(r, lc_ptr[2 * i + 1], lc_ptr[2 * i + 2], term_var, term_coeff, aL, aR, aO, v);
+    sc_mul(o, l, r);
+    st_sc(&aL[i], l); st_sc(&aR[i], r); st_sc(&aO[i], o);
+}
+// a_O = a_L a_R for the multipliers the caller assigned directly (allocate_multiplier / allocate)
+__global__ void __launch_bounds__(128) k_witness_assigned(const uint32_t *__restrict__ order, uint32_t k1, const sc *__restrict__ aL, const sc *__restrict__ aR,
+                                                           sc *__restrict__ aO) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    uint32_t i = order[k];
+    sc l, r, o;
+    ld_sc(l, &aL[i]); ld_sc(r, &aR[i]);
+    sc_mul(o, l, r);
+    st_sc(&aO[i], o);
 }
 
 // ---------------------------------------------------------------- BPG_FLAG_FAST_BLINDING: s_L, s_R on the device

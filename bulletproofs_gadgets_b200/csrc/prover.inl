@@ -146,6 +146,73 @@ extern "C" void bpg_circuit_destroy(bpg_circuit *c) {
     delete c;
 }
 
+// ================================================================ witness evaluation on the device
+extern "C" int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t *lc_ptr, const uint32_t *term_var, const uint8_t *term_coeff,
+                                const uint8_t *v, uint8_t *aL, uint8_t *aR, uint8_t *aO) {
+    if (!ctx || (n && (!lc_ptr || !aL || !aR || !aO)) || (m && !v)) return BPG_E_ARG;
+    if (!n) return BPG_OK;
+    if (n >= (1u << 22) || m >= (1u << 22)) return BPG_E_SIZE;
+    size_t T = lc_ptr[2 * n];
+    if (T && (!term_var || !term_coeff)) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // dependency levels: assigned multipliers (empty pair of linear combinations) are level 0
+    std::vector<uint32_t> level(n, 0);
+    uint32_t depth = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t t0 = lc_ptr[2 * i], t1 = lc_ptr[2 * i + 2];
+        if (t1 < t0 || t1 > T) return BPG_E_ARG;
+        if (t0 == t1) continue;
+        uint32_t lv = 1;
+        for (uint32_t t = t0; t < t1; t++) {
+            uint32_t kind = term_var[t] >> 29, idx = term_var[t] & 0x1FFFFFFFu;
+            if (kind <= 2) { if (idx >= i) return BPG_E_ARG; lv = std::max(lv, level[idx] + 1); } // only earlier multipliers
+            else if (kind == 3) { if (idx >= m) return BPG_E_ARG; }
+            else if (kind != 4) return BPG_E_ARG;
+        }
+        level[i] = lv;
+        depth = std::max(depth, lv);
+    }
+    std::vector<uint32_t> lptr(depth + 2, 0), order(n);
+    for (size_t i = 0; i < n; i++) lptr[level[i] + 1]++;
+    for (uint32_t l = 0; l <= depth; l++) lptr[l + 1] += lptr[l];
+    { std::vector<uint32_t> pos(lptr.begin(), lptr.end() - 1); for (size_t i = 0; i < n; i++) order[pos[level[i]]++] = (uint32_t)i; }
+    cudaStream_t s = ctx->stream;
+    size_t b_w = 3 * 32 * n, b_v = 32 * m, b_ord = 4 * n, b_ptr = 4 * (2 * n + 1), b_tv = 4 * T, b_tc = 32 * T;
+    CTX_TRY(ctx->scratch[8].ensure(b_w + b_v + 64));
+    CTX_TRY(ctx->scratch[11].ensure(b_ord + b_ptr + b_tv + b_tc + 256));
+    sc *d_aL = (sc *)ctx->scratch[8].p, *d_aR = d_aL + n, *d_aO = d_aR + n, *d_v = d_aO + n;
+    uint8_t *d = (uint8_t *)ctx->scratch[11].p;
+    sc *d_tc = (sc *)d;                                  // 32-byte aligned first
+    uint32_t *d_order = (uint32_t *)(d + b_tc), *d_ptr = d_order + n, *d_tv = d_ptr + (2 * n + 1);
+    CUDA_TRY(cudaMemcpyAsync(d_aL, aL, 32 * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_aR, aR, 32 * n, cudaMemcpyHostToDevice, s));
+    if (m) CUDA_TRY(cudaMemcpyAsync(d_v, v, b_v, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), b_ord, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ptr, lc_ptr, b_ptr, cudaMemcpyHostToDevice, s));
+    if (T) {
+        CUDA_TRY(cudaMemcpyAsync(d_tv, term_var, b_tv, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_tc, term_coeff, b_tc, cudaMemcpyHostToDevice, s));
+        k_sc_reduce_inplace<<<LAUNCH_1D(T, 256), 0, s>>>(d_tc, (uint32_t)T);
+        KCHECK();
+    }
+    k_sc_reduce_inplace<<<LAUNCH_1D(2 * n + m, 256), 0, s>>>(d_aL, (uint32_t)(2 * n)); // caller-assigned a_L, a_R (from_bits semantics)
+    KCHECK();
+    if (m) { k_sc_reduce_inplace<<<LAUNCH_1D(m, 256), 0, s>>>(d_v, (uint32_t)m); KCHECK(); }
+    if (lptr[1]) { k_witness_assigned<<<LAUNCH_1D(lptr[1], 128), 0, s>>>(d_order, lptr[1], d_aL, d_aR, d_aO); KCHECK(); }
+    for (uint32_t l = 1; l <= depth; l++) {
+        uint32_t k0 = lptr[l], k1 = lptr[l + 1];
+        if (k1 == k0) continue;
+        k_witness_level<<<LAUNCH_1D(k1 - k0, 128), 0, s>>>(d_order, k0, k1, d_ptr, d_tv, d_tc, d_aL, d_aR, d_aO, d_v);
+        KCHECK();
+    }
+    D2H_TRY(ctx, aL, d_aL, 32 * n, s);
+    D2H_TRY(ctx, aR, d_aR, 32 * n, s);
+    D2H_TRY(ctx, aO, d_aO, 32 * n, s);
+    SYNC_TRY(ctx, s);
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch[8].p, 0, b_w + b_v, s)); // the witness is a prover secret
+    return BPG_OK;
+}
+
 // ================================================================ host scalar helpers
 namespace {
 const sc SC_ONE_H = {{1, 0, 0, 0, 0, 0, 0, 0}};
@@ -563,8 +630,14 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         KCHECK();
         k_ipp_cw<<<1, 32, 0, s>>>(d_small + 24, d_small + 10, d_small + 13);
         KCHECK();
-        k_ipp_expand<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH);
-        KCHECK();
+        // a rank of a sharded proof only needs the expanded scalars (and the per-generator factors behind them) of its own
+        // point range of the original generators; after the late fold the vectors are tiny and every rank keeps all of them
+        uint32_t e0 = 0, e1 = (uint32_t)Ncur;
+        if (shard_on && j < k0) shard_slice((uint32_t)Ncur, ctx->shard_rank, ctx->shard_world, e0, e1);
+        if (e1 > e0) {
+            k_ipp_expand<<<LAUNCH_1D(e1 - e0, 128), 0, s>>>((uint32_t)Ncur, nj, d_a, d_b, d_EG, d_EH, d_sG, d_sH, e0, e1);
+            KCHECK();
+        }
         memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
         plan.ngroups = 2;
         plan.tab = tabcur; plan.ptotal = ptcur;
@@ -581,7 +654,8 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         sc uj = challenge_scalar(t, "u");
         sc uu[2] = {uj, h_inv(uj)};
         CUDA_TRY(cudaMemcpyAsync(d_small + 11, uu, sizeof uu, cudaMemcpyHostToDevice, s));
-        k_ipp_fold<<<LAUNCH_1D(Ncur, 128), 0, s>>>((uint32_t)Ncur, nj, d_small + 11, d_a, d_b, d_EG, d_EH);
+        // (a, b fold in full on every rank; grid = what is needed: the rank's factor range and the lower half of a, b)
+        k_ipp_fold<<<LAUNCH_1D(std::max<size_t>(e1, h), 128), 0, s>>>((uint32_t)Ncur, nj, d_small + 11, d_a, d_b, d_EG, d_EH, e0, e1);
         KCHECK();
     }
     tr.mark("ipp");

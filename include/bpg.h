@@ -142,6 +142,16 @@ int bpg_circuit_create(bpg_ctx *ctx, size_t n_multipliers, size_t m_commitments,
                        const uint32_t *row_ptr, const uint32_t *term_var, const uint8_t *term_coeff, bpg_circuit **out);
 void bpg_circuit_destroy(bpg_circuit *c);
 
+/* Witness evaluation on the device.  Multiplier i created by ConstraintSystem::multiply(left_i, right_i) has
+ * a_L[i] = <left_i>, a_R[i] = <right_i>, a_O[i] = a_L[i] a_R[i], the linear combinations being evaluated over the assignment so
+ * far [cs_buffer.rs:94-97 -> ext Prover::multiply, replayed by prover.rs:102-117].  lc_ptr[2n + 1]: the terms of left_0, right_0,
+ * left_1, ... inside term_var / term_coeff (encoding as for bpg_circuit_create); a term may reference committed values (v, m of
+ * them), One, and multipliers with a SMALLER index only.  Multipliers made by allocate_multiplier / allocate have an empty pair
+ * of combinations: their a_L, a_R are inputs (aL, aR are in/out, n x 32 bytes), a_O is computed.  The dependency graph is
+ * levelised on the host and every level is one launch (independent multipliers in parallel). */
+int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t *lc_ptr, const uint32_t *term_var, const uint8_t *term_coeff,
+                     const uint8_t *v, uint8_t *aL, uint8_t *aR, uint8_t *aO);
+
 /* Prover::new(label) + commit(v_i, blinding_i)* + (constraints) + prove(&bp_gens)  [ext; prover.rs:52-54,93
  * gadget.rs:18-38].  Writes the m commitments to V_out (nullable) and the serialised R1CSProof to `proof`;
  * returns the proof length (> 0) or a negative BPG_E_* code.  ext_rng32 are the 32 bytes the reference's

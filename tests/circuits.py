@@ -81,3 +81,27 @@ def random_dense_instance(n, seed, m=2):
     enc = lambda xs: b"".join(pr.sc_bytes(a) for a in xs)
     return dict(label=b"dense", n=n, vals=enc(vals), blinds=enc(blinds), aL=enc(aL), aR=enc(aR), aO=enc(aO),
                 csr=to_csr(rows), ivals=vals, iblinds=blinds, seed=seed)
+
+
+def host_witness(p):
+    """(a_L, a_R, a_O) of an api.Prover evaluated here with big integers: Prover::eval of every multiply() in creation order
+    (cs_buffer.rs:94-97, prover.rs:102-117).  Test-side checker for the device evaluation (bpg_witness_eval) and the witness
+    source of the CPU-only tests."""
+    n = p.num_vars
+    aL, aR, aO = list(p._in_L), list(p._in_R), [0] * n
+    vals = {0: aL, 1: aR, 2: aO, 3: p.v}
+    tc = bytes(p._w_coeff)
+
+    def ev(t0, t1):
+        acc = 0
+        for t in range(t0, t1):
+            kind, idx = p._w_var[t] >> 29, p._w_var[t] & 0x1FFFFFFF
+            acc += int.from_bytes(tc[32 * t:32 * t + 32], "little") * (1 if kind == 4 else vals[kind][idx])
+        return acc % L
+
+    for i in range(n):
+        t0, t1, t2 = p._w_ptr[2 * i], p._w_ptr[2 * i + 1], p._w_ptr[2 * i + 2]
+        if t2 > t0:
+            aL[i], aR[i] = ev(t0, t1), ev(t1, t2)
+        aO[i] = aL[i] * aR[i] % L
+    return aL, aR, aO

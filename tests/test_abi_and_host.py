@@ -134,7 +134,9 @@ def test_gadget_wiring_fast_builder_equals_reference_shaped_wiring():
     assert prover.get_num_multiplications() == inst["n"] == 972 + 1944 * depth
     assert list(rp) == rp2 and list(tv) == tv2 and tcb == tc2
     enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
-    assert enc(prover.aL) == inst["aL"] and enc(prover.aR) == inst["aR"] and enc(prover.aO) == inst["aO"]
+    from circuits import host_witness
+    aL, aR, aO = host_witness(prover)
+    assert enc(aL) == inst["aL"] and enc(aR) == inst["aR"] and enc(aO) == inst["aO"]
     proof, V = ol.r1cs_prove(inst["label"], 8192, inst["aL"], inst["aR"], inst["aO"], inst["vals"], inst["blinds"], rp, tv, tcb, bytes(32))
     assert ol.r1cs_verify(inst["label"], 8192, inst["n"], V, rp, tv, tcb, proof, bytes(32))
     # the image really is the reference's mimc_hash of the leaf (CLI semantics, prover.rs:171)

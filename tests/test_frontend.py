@@ -11,6 +11,7 @@ import shutil
 import pytest
 
 import oracle_lib as ol
+from circuits import host_witness
 from oracle import pyref as pr
 
 L = pr.L
@@ -27,7 +28,8 @@ def rd(name):
 
 
 def unsatisfied_rows(p):
-    vals = {0: p.aL, 1: p.aR, 2: p.aO, 3: p.v}
+    aL, aR, aO = host_witness(p)
+    vals = {0: aL, 1: aR, 2: aO, 3: p.v}
     rp, tv, tc = p.csr()
     bad = 0
     for r in range(len(rp) - 1):
@@ -112,6 +114,47 @@ def test_cli_fixture_prover_then_verifier(name, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SIZES))
+def test_device_witness_evaluation_matches_big_integers(name):
+    """SURVEY 8 f-3: Prover::eval of every multiply() (cs_buffer.rs:94-97 replayed by prover.rs:102-117) runs on the device,
+    level by level; a_L, a_R, a_O must equal the host big-integer evaluation for every reference fixture"""
+    import bulletproofs_gadgets_b200 as bpg
+    from bulletproofs_gadgets_b200 import frontend as fe
+    run = fe.ProverRun(name.encode(), rd(name + ".gadgets"), rd(name + ".inst"), rd(name + ".wtns"), test_seed=1, ctx=bpg.Context.default())
+    assert run.prover.witness() == host_witness(run.prover)
+
+
+@pytest.mark.gpu
+def test_device_witness_evaluation_edge_cases():
+    """no multipliers; only assigned multipliers; a pending half-allocated multiplier; unreduced inputs; a deep chain; a
+    combination referencing a LATER multiplier is rejected (BPG_E_ARG), never evaluated"""
+    import ctypes as C
+    import random
+
+    import bulletproofs_gadgets_b200 as bpg
+    ctx = bpg.Context.default()
+    rnd = random.Random(5)
+    p = bpg.Prover.new(b"w", ctx=ctx)
+    assert p.witness() == ([], [], [])
+    _, v0 = p.commit(rnd.randrange(L), 1)
+    p.allocate_multiplier((L - 1, L - 1))
+    x = p.allocate(7)
+    assert p.witness() == host_witness(p) and p.witness()[2] == [1, 0]
+    p.allocate(9)
+    cur = [(x, 3), (v0, L - 2), (bpg.api.ONE, rnd.randrange(L))]
+    for _ in range(300):
+        _, r, o = p.multiply(cur, cur + [(bpg.api.ONE, 1)])
+        cur = [(o, rnd.randrange(L)), (r, 5), (v0, 1)]
+    w = p.witness()
+    assert w == host_witness(p) and w[2][1] == 63
+    n = 3
+    ptr = (C.c_uint32 * (2 * n + 1))(0, 0, 0, 1, 2, 2, 2)
+    tv = (C.c_uint32 * 2)((0 << 29) | 2, 4 << 29)  # multiplier 1 references a_L[2]
+    bufs = [C.create_string_buffer(32 * n) for _ in range(3)]
+    assert ctx.lib.bpg_witness_eval(ctx.h, n, 0, ptr, tv, bytes(64), None, *bufs) == -4  # BPG_E_ARG
+
+
+@pytest.mark.gpu
 def test_cli_falsified_statements_are_rejected_and_oracle_agrees(tmp_path):
     """verdict parity on statements that are false (the reference's is_err unit cases): the GPU verifier and the CPU oracle
     verifier both reject; the GPU proof bytes of a true statement equal the oracle prover's bytes"""
@@ -136,6 +179,8 @@ def test_cli_falsified_statements_are_rejected_and_oracle_agrees(tmp_path):
         p = run.prover
         rp, tv, tc = p.csr()
         enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
-        oproof, oV = ol.r1cs_prove(b"case", 1 << 12, enc(p.aL), enc(p.aR), enc(p.aO), enc(p.v), enc(p.v_blinding), rp, tv, tc, bytes([k]) * 32)
+        aL, aR, aO = p.witness_bytes()  # evaluated on the device (bpg_witness_eval) ...
+        assert (aL, aR, aO) == tuple(enc(x) for x in host_witness(p))  # ... equal to the big-integer evaluation
+        oproof, oV = ol.r1cs_prove(b"case", 1 << 12, aL, aR, aO, enc(p.v), enc(p.v_blinding), rp, tv, tc, bytes([k]) * 32)
         assert oproof == proof
         assert ol.r1cs_verify(b"case", 1 << 12, p.get_num_multiplications(), oV, rp, tv, tc, proof, bytes(32)) is want
