@@ -588,7 +588,9 @@ def run_ours(args):
     per_gpu = cores / max(world, 1)
     # Concurrent provers per GPU: a 2^20 proof is ~55 ms of device work and ~0.1 s of (lane-shared) host RNG, so a handful of
     # proofs in flight hide the host side; each prover holds ~1.3 GB of HBM workspace.
-    P = args.provers if args.provers > 0 else (8 if per_gpu >= 8 else 6)
+    # (measured on a 16-core host, byte-exact: 8 / 12 / 24 provers -> 11 / 15.0 / 18.3 proofs/s: below ~20 provers a lane waits for
+    # its next RNG stream -- 0.75 s however many lanes share the SIMD registers -- longer than its turn on the GPU takes)
+    P = args.provers if args.provers > 0 else (24 if per_gpu >= 8 else 16)
     blocking = P * world > cores
     ctx0 = bpg.Context(local)
     ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)

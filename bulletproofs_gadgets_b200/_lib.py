@@ -7,6 +7,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbpg.so")
+if os.environ.get("BPG_LIB"):  # A/B builds of the same sources (development aid), e.g. BPG_LIB=libbpg_pad.so
+    LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), os.environ["BPG_LIB"])
 
 OK, E_CUDA, E_SIZE, E_DECOMPRESS, E_ARG, E_FORMAT, E_NOMEM, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
 FLAG_LEGACY_FRAMING, FLAG_FAST_BLINDING, FLAG_WITNESS_ON_DEVICE = 1, 2, 4

@@ -287,6 +287,8 @@ __device__ __forceinline__ void msm_load_entry(ge_an &a, const ge_an *__restrict
 }
 
 // partial slot layout: partial[2*chunk + 0] = run touching the chunk start, [2*chunk + 1] = run touching the chunk end only
+// (Tried and dropped, profiles/r02_accumulate_variants.jsonl: prefetch.global.L1 / .L2 of the next pair's entry one iteration
+// ahead -- 12.9 -> 9.6 G additions/s; entries padded to one aligned 128-byte line -- DRAM traffic down, time unchanged.)
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets, uint32_t nbuckets,
                                                          const ge_an *__restrict__ tab, ge *__restrict__ buckets, ge *__restrict__ partial, uint32_t CH) {
     uint32_t M = offsets[nbuckets];
@@ -568,49 +570,47 @@ __global__ void __launch_bounds__(256) k_mat_digits(uint32_t N, uint32_t nprime,
         }
     }
 }
-// One 32-thread block per output.  Lane = (set, segment): set = lane >> 3 (0 low, 1 high), segment s = lane & 7 covers
-// buckets 16 s + 1 .. 16 s + 16.  Running sums give seg_sum = sum T_b and seg_w = sum (b - 16 s) T_b; the lane's value is
-// seg_w + 16 s * seg_sum; lanes of a set are tree-summed, and the output is low + 2^8 high.
+// One 32-thread block per output.  Lane = (set, segment): set = lane >> 4 (0 low, 1 high), segment s = lane & 15 covers
+// buckets 8 s + 1 .. 8 s + 8.  Running sums give seg_sum = sum T_b and seg_w = sum (b - 8 s) T_b; the lane's value is
+// seg_w + 8 s * seg_sum; the 16 lanes of a set are tree-summed, and the output is low + 2^8 high.
 __global__ void __launch_bounds__(32) k_mat_reduce(const ge *__restrict__ buckets, uint32_t nout, ge *__restrict__ out) {
-    __shared__ ge smem[16];
+    __shared__ ge smem[32];
     uint32_t o = blockIdx.x, lane = threadIdx.x;
     if (o >= nout) return;
-    if (lane < 16) {
-        uint32_t set = lane >> 3, seg = lane & 7;
-        const ge *B = buckets + ((size_t)2 * o + set) * BPG_MAT_NB + 16u * seg;
-        ge run, acc, q;
-        ge_identity(run); ge_identity(acc);
+    uint32_t set = lane >> 4, seg = lane & 15;
+    const ge *B = buckets + ((size_t)2 * o + set) * BPG_MAT_NB + 8u * seg;
+    ge run, acc, q;
+    ge_identity(run); ge_identity(acc);
 #pragma unroll 1
-        for (int b = 16; b >= 1; b--) {
-            ld_ge(q, &B[b]);
-            ge_add_ilp(run, run, q);
-            ge_add_ilp(acc, acc, run);
-        }
-        // acc += 16 * seg * run
-        ge m;
-        ge_small_mul(m, seg, run);
-#pragma unroll 1
-        for (int k = 0; k < 4; k++) ge_dbl_ilp(m, m);
-        ge_add_ilp(acc, acc, m);
-        st_ge(&smem[lane], acc);
+    for (int b = 8; b >= 1; b--) {
+        ld_ge(q, &B[b]);
+        ge_add_ilp(run, run, q);
+        ge_add_ilp(acc, acc, run);
     }
+    // acc += 8 * seg * run
+    ge m;
+    ge_small_mul(m, seg, run);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) ge_dbl_ilp(m, m);
+    ge_add_ilp(acc, acc, m);
+    st_ge(&smem[lane], acc);
     __syncwarp();
-    for (int s2 = 4; s2 > 0; s2 >>= 1) {
-        if (lane < 16 && (lane & 7) < (uint32_t)s2) {
-            ge a, b;
-            ld_ge(a, &smem[lane]); ld_ge(b, &smem[lane + s2]);
-            ge_add_ilp(a, a, b);
-            st_ge(&smem[lane], a);
+    for (int s2 = 8; s2 > 0; s2 >>= 1) {
+        if (seg < (uint32_t)s2) {
+            ge b;
+            ld_ge(b, &smem[lane + s2]);
+            ge_add_ilp(acc, acc, b);
+            st_ge(&smem[lane], acc);
         }
         __syncwarp();
     }
     if (lane == 0) {
-        ge lo, hi;
-        ld_ge(lo, &smem[0]); ld_ge(hi, &smem[8]);
+        ge hi;
+        ld_ge(hi, &smem[16]);
 #pragma unroll 1
         for (int k = 0; k < 8; k++) ge_dbl_ilp(hi, hi);
-        ge_add_ilp(lo, lo, hi);
-        st_ge(&out[o], lo);
+        ge_add_ilp(acc, acc, hi);
+        st_ge(&out[o], acc);
     }
 }
 // Latency-lean reduction of the same 2 x 129 bucket layout for the few groups of a SMALL MSM (late IPP rounds: 2 groups,

@@ -182,6 +182,30 @@ __global__ void __launch_bounds__(256) k_bench(uint32_t *out, int iters) {
 #pragma unroll
         for (int i = 0; i < 8; i++) x ^= a.v[i] ^ b.v[i];
         if (x == 0x12345678u) out[t] = x;
+    } else if (VAR == 4) {
+        // warp-specialised: even warps run the integer chain, odd warps the DFMA chain (nothing shared but the SM).  With
+        // independent pipes this takes max(T_int, T_dfma) / 2, with a shared issue port (T_int + T_dfma) / 2.
+        if ((threadIdx.x >> 5) & 1) {
+            fd a, b;
+#pragma unroll
+            for (int i = 0; i < 5; i++) { a.v[i] = (double)((t * 2654435761u + i) & 0xFFFFFu) * 1048576.0 + 3.0; b.v[i] = (double)((t * 40503u + 77u * i + 1) & 0xFFFFFu) * 524288.0 + 5.0; }
+#pragma unroll 1
+            for (int it = 0; it < iters; it++) { fd_mul(a, a, b); fd_mul(b, b, a); }
+            double x = 0;
+#pragma unroll
+            for (int i = 0; i < 5; i++) x += a.v[i] + b.v[i];
+            if (x == 12345.678) out[t] = 1;
+        } else {
+            fe a, b;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a.v[i] = t * 2654435761u + i; b.v[i] = t * 40503u + 77u * i + 1; }
+#pragma unroll 1
+            for (int it = 0; it < iters; it++) { fe_mul(a, a, b); fe_mul(b, b, a); }
+            uint32_t x = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) x ^= a.v[i] ^ b.v[i];
+            if (x == 0x12345678u) out[t] = x;
+        }
     } else if (VAR == 3) {
         // co-issue: one IMAD.WIDE chain and one DFMA chain per thread, independent of each other (upper bound of what a
         // mixed addition that splits its 7 multiplications over both pipes could reach; counted as 2 + 2 fe_mul per iteration)
@@ -215,6 +239,7 @@ __global__ void __launch_bounds__(256) k_bench(uint32_t *out, int iters) {
     }
 }
 
+static int g_reps = 5; // 1 under ncu (`dfma_bench ncu`): one launch per variant
 template <int VAR>
 static void bench(const char *name, int sms, int blocks_per_sm, int threads, int iters) {
     uint32_t *d;
@@ -224,7 +249,7 @@ static void bench(const char *name, int sms, int blocks_per_sm, int threads, int
     k_bench<VAR><<<sms * blocks_per_sm, threads>>>(d, 8);
     cudaDeviceSynchronize();
     float best = 1e30f;
-    for (int rep = 0; rep < 5; rep++) {
+    for (int rep = 0; rep < g_reps; rep++) {
         cudaEventRecord(e0);
         k_bench<VAR><<<sms * blocks_per_sm, threads>>>(d, iters);
         cudaEventRecord(e1);
@@ -238,7 +263,9 @@ static void bench(const char *name, int sms, int blocks_per_sm, int threads, int
     cudaFree(d);
 }
 
-int main() {
+int main(int argc, char **argv) {
+    const bool ncu_mode = argc > 1;
+    if (ncu_mode) g_reps = 1;
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     int sms = p.multiProcessorCount;
@@ -253,10 +280,12 @@ int main() {
     printf("{\"check\": \"dfma fe_mul vs integer fe_mul, 64 x 128 threads x 64 chained products\", \"mismatch_independent\": %u, \"mismatch_chained_hi\": %u, \"cuda\": \"%s\"}\n",
            h_m[0], h_m[1], cudaGetErrorString(e));
     for (int bps : {2, 4, 8}) {
+        if (ncu_mode && bps != 4) continue;
         bench<2>("imad_wide_8x32", sms, bps, 256, 400);
         bench<0>("dfma_5x51_independent", sms, bps, 256, 400);
         bench<1>("dfma_5x51_chained_hi", sms, bps, 256, 400);
         bench<3>("co_issue_imad_chain_plus_dfma_chain", sms, bps, 256, 400);
+        bench<4>("warp_specialised_even_imad_odd_dfma", sms, bps, 256, 400);
     }
     return 0;
 }

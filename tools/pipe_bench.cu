@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #define ITERS 4096
 template <int MODE>
-__global__ void __launch_bounds__(256) k(uint64_t *out) {
+__device__ __forceinline__ void body(uint64_t *out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
     uint32_t x = t * 2654435761u + 1, y = t * 40503u + 3;
@@ -56,6 +56,17 @@ __global__ void __launch_bounds__(256) k(uint64_t *out) {
     uint64_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ (uint64_t)(d0 + d1 + d2 + d3);
     if (r == 0x1234567812345678ULL) out[t] = r;
 }
+// MODE < 16: every warp runs the same loop.  MODE = 16 + 4 A + B (A, B in {0: IMAD.WIDE, 1: IMAD, 3: DFMA, 2 -> 4: IADD3 carry}):
+// warp-specialised mix -- even warps run loop A, odd warps loop B, nothing shared between them but the SM.  If the two pipes
+// issue independently the mix takes max(T_A, T_B) / 2, if they share an issue port (T_A + T_B) / 2.
+template <int MODE>
+__global__ void __launch_bounds__(256) k(uint64_t *out) {
+    if (MODE < 16) body<MODE>(out);
+    else {
+        constexpr int A = ((MODE - 16) >> 2) == 2 ? 4 : ((MODE - 16) >> 2), B = ((MODE - 16) & 3) == 2 ? 4 : ((MODE - 16) & 3);
+        if ((threadIdx.x >> 5) & 1) body<B>(out); else body<A>(out);
+    }
+}
 template <int MODE>
 static void run(const char *name, double ops_per_iter, int sms, int clk_khz) {
     uint64_t *d;
@@ -90,5 +101,10 @@ int main() {
     run<2>("imad_hi_u32", 8, p.multiProcessorCount, clk);
     run<3>("dfma_f64", 8, p.multiProcessorCount, clk);
     run<4>("iadd3_carry", 8, p.multiProcessorCount, clk);
+    run<16 + 4 * 0 + 3>("mix_even_imad_wide_odd_dfma", 8, p.multiProcessorCount, clk);
+    run<16 + 4 * 0 + 2>("mix_even_imad_wide_odd_iadd3", 8, p.multiProcessorCount, clk);
+    run<16 + 4 * 3 + 2>("mix_even_dfma_odd_iadd3", 8, p.multiProcessorCount, clk);
+    run<16 + 4 * 0 + 1>("mix_even_imad_wide_odd_imad_lo", 8, p.multiProcessorCount, clk);
+    run<16 + 4 * 3 + 1>("mix_even_dfma_odd_imad_lo", 8, p.multiProcessorCount, clk);
     return 0;
 }
