@@ -233,20 +233,25 @@ def msm_var_sweep(ctx, sizes, reps=3, cpu_sizes=(), cores=1):
     raw = rng.integers(0, 256, size=(maxn, 32), dtype=np.uint8)
     raw[:, 31] &= 0x0F
     sc = raw.tobytes()
+    # the caller's buffers are page-locked (bpg_host_alloc), as a host application feeding large MSMs would keep them
+    h_sc, hh_sc = ctx.host_alloc(sc)
+    h_pt, hh_pt = ctx.host_alloc(pts[:32 * maxn])
     for n in sizes:
-        sn, pn = sc[:32 * n], pts[:32 * n]  # (slicing copies: not inside the timed loop)
-        got = ctx.msm(sn, pn)
+        got = ctx.msm(h_sc, h_pt, n)
         t0 = time.perf_counter()
         for _ in range(reps):
-            ctx.msm(sn, pn)
+            ctx.msm(h_sc, h_pt, n)
         ms = (time.perf_counter() - t0) * 1e3 / reps
-        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3, "h2d_bytes": 64 * n}
+        out[str(n)] = {"ms": ms, "mpoints_per_s": n / ms / 1e3, "h2d_bytes": 64 * n, "host_buffers": "page-locked"}
         if n in cpu_sizes:
+            sn, pn = sc[:32 * n], pts[:32 * n]
             ol.lib().bpo_set_threads(cores)
             t0 = time.perf_counter()
             want = ol.msm(sn, pn)
             dt = time.perf_counter() - t0
             out[str(n)].update({"cpu_mpoints_per_s": n / dt / 1e6, "cpu_cores": cores, "equals_oracle": got == want})
+    ctx.host_free(hh_sc)
+    ctx.host_free(hh_pt)
     return out
 
 
@@ -492,7 +497,7 @@ def batch_verify_config5(bpg, ctx, dist, local, rank, world, total, cores):
 class ProverLane:
     """one host thread's private context: own bpg_ctx (stream, workspace), circuit copy, own witness (host + HBM-resident)"""
 
-    def __init__(self, bpg, gadgets, device, inst, cap):
+    def __init__(self, bpg, gadgets, device, inst, cap, keep_bytes=True):
         import ctypes as C
         self.ctx = bpg.Context(device)
         self.ctx.gens_ensure(cap)
@@ -500,15 +505,29 @@ class ProverLane:
         self.circ = gadgets.Circuit(self.ctx, inst["n"], inst["m"], inst["csr"])
         n = inst["n"]
         self.d_w = self.ctx.dev_alloc(3 * 32 * n)
-        self.ctx.dev_upload(self.d_w, inst["aL"] + inst["aR"] + inst["aO"])
+        for k, key in enumerate(("aL", "aR", "aO")):
+            self.ctx.dev_upload(C.c_void_p(self.d_w.value + 32 * n * k), inst[key])
         self.dev_inst = dict(inst)
         self.dev_inst["aL"], self.dev_inst["aR"], self.dev_inst["aO"] = (C.cast(C.c_void_p(self.d_w.value + 32 * n * k), C.c_char_p) for k in range(3))
 
+        # the end-to-end leg hands the library HOST buffers: the witness sits in page-locked host memory (bpg_host_alloc), as
+        # the bench contract's "inputs from pinned host memory" and as a Rust caller would keep its assignment vectors
+        self.host_inst = dict(inst)
+        self.h_w = []
+        for k in ("aL", "aR", "aO"):
+            ptr, handle = self.ctx.host_alloc(inst[k])
+            self.host_inst[k] = ptr
+            self.h_w.append(handle)
+            if not keep_bytes:
+                inst[k] = None  # the pageable copy is not needed again (48 lanes x 100 MB)
+
     def prove(self, ext, flags, resident):
-        return self.circ.prove(self.dev_inst if resident else self.inst, ext, flags)
+        return self.circ.prove(self.dev_inst if resident else self.host_inst, ext, flags)
 
     def close(self):
         self.circ.close()
+        for h in self.h_w:
+            self.ctx.host_free(h)
         self.ctx.dev_free(self.d_w)
         self.ctx.close()
 
@@ -518,7 +537,7 @@ class LaneSet:
 
     def __init__(self, bpg, gadgets, device, insts, cap, rank):
         from concurrent.futures import ThreadPoolExecutor
-        self.lanes = [ProverLane(bpg, gadgets, device, inst, cap) for inst in insts]
+        self.lanes = [ProverLane(bpg, gadgets, device, inst, cap, keep_bytes=(k == 0)) for k, inst in enumerate(insts)]
         self.P = len(self.lanes)
         self.pool = ThreadPoolExecutor(max_workers=self.P)
         self.rank = rank
@@ -588,9 +607,10 @@ def run_ours(args):
     per_gpu = cores / max(world, 1)
     # Concurrent provers per GPU: a 2^20 proof is ~55 ms of device work and ~0.1 s of (lane-shared) host RNG, so a handful of
     # proofs in flight hide the host side; each prover holds ~1.3 GB of HBM workspace.
-    # (measured on a 16-core host, byte-exact: 8 / 12 / 24 provers -> 11 / 15.0 / 18.3 proofs/s: below ~20 provers a lane waits for
-    # its next RNG stream -- 0.75 s however many lanes share the SIMD registers -- longer than its turn on the GPU takes)
-    P = args.provers if args.provers > 0 else (24 if per_gpu >= 8 else 16)
+    # (measured on a 16-core host, byte-exact: 8 / 12 / 24 / 32 / 48 provers -> 11 / 15.0 / 19.6 / 20.1 / 21.4 proofs/s: a lane
+    # waits for its next RNG stream -- 0.75 s however many lanes share the SIMD registers -- unless its turn on the GPU takes
+    # longer than that; at 48 the byte-exact rate reaches the fast-blinding rate, i.e. the GPU is the limit)
+    P = args.provers if args.provers > 0 else 48
     blocking = P * world > cores
     ctx0 = bpg.Context(local)
     ctx0.lib.bpg_set_blocking_sync(1 if blocking else 0)
@@ -811,7 +831,7 @@ def config1_throughput(bpg, gadgets, local, ctx0, cores, args):
     P = 64
     ctx0.lib.bpg_set_blocking_sync(1 if P > cores else 0)
     inst = gadgets.merkle_path_instance(32, seed=4, ctx=ctx0)
-    lanes = LaneSet(bpg, gadgets, local, [inst] * P, 1 << 16, 0)
+    lanes = LaneSet(bpg, gadgets, local, [dict(inst) for _ in range(P)], 1 << 16, 0)
     RES = bpg._lib.FLAG_WITNESS_ON_DEVICE
     lanes.timed(RES, True, 4)
     ms, launches = lanes.timed(RES, True, 6)

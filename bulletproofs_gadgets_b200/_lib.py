@@ -63,6 +63,8 @@ SYMBOLS = {
     "bpg_host_rng_draw64": (_i32, [_u8p, _sz, _u8p, _sz, _sz, _i32, _u8p]),
     "bpg_dev_alloc": (_i32, [_vp, _sz, C.POINTER(_vp)]),
     "bpg_dev_free": (_i32, [_vp, _vp]),
+    "bpg_host_alloc": (_i32, [_vp, _sz, C.POINTER(_vp)]),
+    "bpg_host_free": (_i32, [_vp, _vp]),
     "bpg_dev_upload": (_i32, [_vp, _vp, _u8p, _sz]),
     "bpg_dev_download": (_i32, [_vp, _u8p, _vp, _sz]),
     "bpg_event_record": (_i32, [_vp, _i32]),

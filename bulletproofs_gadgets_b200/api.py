@@ -83,9 +83,10 @@ class Context:
         self.check(self.lib.bpg_pedersen_commit(self.h, v, r, n, out))
         return out.raw[:32 * n]
 
-    def msm(self, scalars, points):
+    def msm(self, scalars, points, n=None):
+        """variable-base MSM; scalars / points: bytes, or host pointers (e.g. from host_alloc) with n given"""
         out = C.create_string_buffer(32)
-        self.check(self.lib.bpg_msm(self.h, scalars, points, len(scalars) // 32, out))
+        self.check(self.lib.bpg_msm(self.h, scalars, points, len(scalars) // 32 if n is None else n, out))
         return out.raw
 
     def msm_gens(self, sG, sH, n, offset=0, extra_scalars=b"", extra_points=b""):
@@ -221,6 +222,17 @@ class Context:
         p = C.c_void_p()
         self.check(self.lib.bpg_dev_alloc(self.h, nbytes, C.byref(p)))
         return p
+
+    def host_alloc(self, data):
+        """page-locked host copy of `data` (bpg_host_alloc); returns (pointer usable wherever a host buffer is expected, handle
+        for host_free)"""
+        p = C.c_void_p()
+        self.check(self.lib.bpg_host_alloc(self.h, len(data), C.byref(p)))
+        C.memmove(p, data, len(data))
+        return C.cast(p, C.c_char_p), p
+
+    def host_free(self, p):
+        self.check(self.lib.bpg_host_free(self.h, p))
 
     def dev_free(self, p):
         self.check(self.lib.bpg_dev_free(self.h, p))

@@ -163,6 +163,8 @@ extern "C" int bpg_sync(bpg_ctx *ctx) { if (!ctx) return BPG_E_ARG; SYNC_TRY(ctx
 
 extern "C" int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr) { if (!ctx || !d_ptr) return BPG_E_ARG; CUDA_TRY(cudaSetDevice(ctx->device)); CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 1)); return BPG_OK; }
 extern "C" int bpg_dev_free(bpg_ctx *ctx, void *d_ptr) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaFree(d_ptr)); return BPG_OK; }
+extern "C" int bpg_host_alloc(bpg_ctx *ctx, size_t bytes, void **h_ptr) { if (!ctx || !h_ptr) return BPG_E_ARG; CUDA_TRY(cudaSetDevice(ctx->device)); CUDA_TRY(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocPortable)); return BPG_OK; }
+extern "C" int bpg_host_free(bpg_ctx *ctx, void *h_ptr) { if (!ctx) return BPG_E_ARG; CUDA_TRY(cudaFreeHost(h_ptr)); return BPG_OK; }
 extern "C" int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!ctx) return BPG_E_ARG;
     CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -615,7 +617,13 @@ int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t npri
     if (sharded) shard_slice(N, ctx->shard_rank, ctx->shard_world, p0, p1);
     uint32_t nt = 2 * (p1 - p0);
     CTX_TRY(msm_bucketize(ctx, s, nb, (size_t)nt * BPG_NWIN * 2, nt != 0, ctx->tab, lean, [&](int scatter, uint32_t *cc, uint32_t *sorted) {
-        if (scatter) k_mat_digits<1><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, p0, p1, cc, sorted);
+        // one block per output, no global atomics (BPG_MAT_BLOCK=0 keeps the term-parallel kernels for A/B runs)
+        static const int mat_block = [] { const char *e = getenv("BPG_MAT_BLOCK"); return e ? atoi(e) : 1; }();
+        if (mat_block) {
+            if (scatter) k_mat_block<1><<<nout, 256, 0, s>>>(p0, p1, nprime, cap, ptotal, d_EG, d_EH, nullptr, (const uint32_t *)ctx->offsets.p, sorted);
+            else k_mat_block<0><<<nout, 256, 0, s>>>(p0, p1, nprime, cap, ptotal, d_EG, d_EH, cc, nullptr, nullptr);
+        }
+        else if (scatter) k_mat_digits<1><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, p0, p1, cc, sorted);
         else k_mat_digits<0><<<LAUNCH_1D(nt, 256), 0, s>>>(N, nprime, cap, ptotal, d_EG, d_EH, p0, p1, cc, sorted);
     }));
     k_mat_reduce<<<nout, 32, 0, s>>>((const ge *)ctx->buckets.p, nout, (ge *)ctx->mat_pts.p);

@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(1024, 1) k_msm_scatter_smem(msm_params P, uint
     }
 }
 
+// (Tried and dropped, profiles/r02_sort_variants.jsonl: a two-pass bin sort for MSMs beyond the reach of k_msm_scatter_smem --
+// partition the pairs into bins of 32 buckets with shared-memory counters per tile, then distribute every 8 192-record slice
+// with one global atomic per (slice, bucket).  0.46 + 0.42 ms against 0.70 ms for the plain cursor-ordered scatter at 2^21 terms.)
 // Exclusive scan of counts[0..n) into offsets[0..n] and cursor[0..n).  Tiles of 1024 counters, one 256-thread block
 // each (small blocks so the scan can run in the register space left over by another context's accumulate grid).
 // A block publishes its tile total, then sums the totals of all earlier tiles (<= 128 values, one coalesced read);
@@ -568,6 +571,49 @@ __global__ void __launch_bounds__(256) k_mat_digits(uint32_t N, uint32_t nprime,
                 atomicAdd(&counts_or_cursor[bkt], 1u);
             }
         }
+    }
+}
+// The same two passes with ONE BLOCK PER OUTPUT: all pairs of output o (terms p = o, o + n', o + 2n', ... inside this rank's
+// point range [p0, p1)) land in the 2 x 129 buckets of that output, so the block counts them in shared memory,
+// writes the counts without atomics, and -- after the scan -- places the pairs with shared-memory ranks: no global atomics and
+// every block writes one contiguous 32 KB region (k_mat_digits: 2 x 67 M global atomics, 0.31 + 1.44 ms of a 2^20 proof).
+template <int PLACE>
+__global__ void __launch_bounds__(256) k_mat_block(uint32_t p0, uint32_t p1, uint32_t nprime, uint32_t cap, uint32_t ptotal, const sc *__restrict__ EG,
+                                                   const sc *__restrict__ EH, uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ sorted) {
+    __shared__ uint32_t scnt[2 * BPG_MAT_NB];
+    const uint32_t out = blockIdx.x; // [0, n') : G side, [n', 2 n') : H side
+    const bool isH = out >= nprime;
+    const uint32_t q = isH ? out - nprime : out;
+    const uint32_t base = 2u * out * BPG_MAT_NB;
+    for (uint32_t i = threadIdx.x; i < 2 * BPG_MAT_NB; i += blockDim.x) scnt[i] = PLACE ? offsets[base + i] : 0u;
+    __syncthreads();
+    const uint32_t kfirst = p0 > q ? (p0 - q + nprime - 1) / nprime : 0u; // first term of this output inside [p0, p1)
+    for (uint32_t p = q + nprime * (kfirst + threadIdx.x); p < p1; p += nprime * blockDim.x) {
+        sc k;
+        ld_sc(k, isH ? &EH[p] : &EG[p]);
+        int d[16];
+        sc_digits16(d, k);
+        const uint32_t pidx = p + (isH ? cap : 0u);
+#pragma unroll
+        for (int w = 0; w < 16; w++) {
+            int dw = d[w];
+            if (dw == 0) continue;
+            int dl = ((dw + 128) & 255) - 128;
+            int dh = (dw - dl) >> 8;
+            uint32_t ent = (uint32_t)w * ptotal + pidx;
+#pragma unroll
+            for (int part = 0; part < 2; part++) {
+                int dd = part ? dh : dl;
+                if (dd == 0) continue;
+                uint32_t mag = dd < 0 ? (uint32_t)(-dd) : (uint32_t)dd;
+                uint32_t pos = atomicAdd(&scnt[part * BPG_MAT_NB + mag], 1u);
+                if (PLACE) sorted[pos] = ent | (dd < 0 ? 0x80000000u : 0u);
+            }
+        }
+    }
+    if (!PLACE) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < 2 * BPG_MAT_NB; i += blockDim.x) counts[base + i] = scnt[i];
     }
 }
 // One 32-thread block per output.  Lane = (set, segment): set = lane >> 4 (0 low, 1 high), segment s = lane & 15 covers

@@ -599,12 +599,14 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
     // n' = N >> k0 folded generators are materialised and the remaining rounds run over them (EG = EH = 1 again).
     int k0 = lgN; // no late fold
     bool late = (flags & BPG_FLAG_FORCE_LATE_FOLD) ? lgN >= 2 : (!(flags & BPG_FLAG_NO_LATE_FOLD) && lgN >= 15);
-    // folded generators kept per vector: 512, or N / 256 for large circuits (measured at N = 2^16: 256 / 512 / 1024 / 2048 ->
+    // folded generators kept per vector: 512, or N / 128 for large circuits (round 1: N / 256) (measured at N = 2^16: 256 / 512 / 1024 / 2048 ->
     // 309 / 315 / 303 / 242 proofs/s; single proof at N = 2^20: 512 / 2048 / 4096 / 8192 -> 71.7 / 65.9 / 64.3 / 63.4 ms,
-    // N = 2^19: 48.9 / 46.3 / 45.8 / 46.5 ms).  BPG_LATE_FOLD_LG overrides the log2 for experiments.
+    // N = 2^19: 48.9 / 46.3 / 45.8 / 46.5 ms).  Round 2, after the full-warp k_mat_reduce and the block-per-output sort of the
+    // materialisation: N / 128 (single proof at N = 2^20: 4096 / 8192 / 16384 -> 62.8 / 61.0 / 61.7 ms; 24 provers: 17.7 / 18.9 /
+    // 18.6 proofs/s).  BPG_LATE_FOLD_LG overrides the log2 for experiments.
     static int late_lg_env = -1;
     if (late_lg_env < 0) { const char *e = getenv("BPG_LATE_FOLD_LG"); late_lg_env = e ? atoi(e) : 0; if (late_lg_env < 1 || late_lg_env > 14) late_lg_env = 0; }
-    int late_lg = late_lg_env ? late_lg_env : std::max(9, lgN - 8);
+    int late_lg = late_lg_env ? late_lg_env : std::max(9, lgN - 7);
     if (shard_on) while (late_lg > 1 && ((size_t)2 << late_lg) * sizeof(ge) > ctx->shard_cap) late_lg--; // partial outputs must fit one exchange
     if (late) k0 = std::max(1, lgN - late_lg);
     size_t Ncur = N;                       // generators of the current basis

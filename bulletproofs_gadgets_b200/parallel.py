@@ -112,7 +112,7 @@ def disable_comm(ctx):
 
 
 # ---------------------------------------------------------------- one proof over several ranks (BASELINE configs[3])
-_SHARD_CAP = 2 << 20  # bytes of partial points per exchange: the late fold sends 2 x (N / 256) outputs x 128 B = 1 MiB at N = 2^20
+_SHARD_CAP = 2 << 20  # bytes of partial points per exchange: the late fold sends 2 x (N / 128) outputs x 128 B = 2 MiB at N = 2^20
 
 
 def enable_sharded_prover(ctx, device):

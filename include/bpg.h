@@ -204,6 +204,12 @@ int bpg_dev_alloc(bpg_ctx *ctx, size_t bytes, void **d_ptr);
 int bpg_dev_free(bpg_ctx *ctx, void *d_ptr);
 int bpg_dev_upload(bpg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int bpg_dev_download(bpg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* Page-locked host memory for callers that hand large host vectors to bpg_r1cs_prove (a_L, a_R, a_O: 96 bytes per
+ * multiplier).  Every entry point accepts ordinary (pageable) host pointers; from a buffer allocated here the upload is one
+ * asynchronous DMA at full PCIe rate instead of a staged copy the calling thread has to wait for (the witness of a
+ * 2^20-multiplier proof: ~2 ms instead of ~9 ms).  The Rust side would keep its Vec<Scalar> assignment in such a buffer. */
+int bpg_host_alloc(bpg_ctx *ctx, size_t bytes, void **h_ptr);
+int bpg_host_free(bpg_ctx *ctx, void *h_ptr);
 
 /* timing on the library's own stream: record event slot i (0..15), elapsed milliseconds between two slots
  * (slots 14 / 15 are recorded by bpg_mimc_sponge_batch around its kernel) */

@@ -73,6 +73,8 @@ extern "C" {
     pub fn bpg_dev_free(ctx: *mut BpgCtx, d_ptr: *mut c_void) -> i32;
     pub fn bpg_dev_upload(ctx: *mut BpgCtx, d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> i32;
     pub fn bpg_dev_download(ctx: *mut BpgCtx, h_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> i32;
+    pub fn bpg_host_alloc(ctx: *mut BpgCtx, bytes: usize, h_ptr: *mut *mut c_void) -> i32;
+    pub fn bpg_host_free(ctx: *mut BpgCtx, h_ptr: *mut c_void) -> i32;
     pub fn bpg_event_record(ctx: *mut BpgCtx, slot: i32) -> i32;
     pub fn bpg_event_elapsed_ms(ctx: *mut BpgCtx, slot_a: i32, slot_b: i32, ms: *mut f32) -> i32;
     pub fn bpg_prof_enable(ctx: *mut BpgCtx, on: i32) -> i32;

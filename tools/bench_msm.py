@@ -14,7 +14,7 @@ ctx.gens_ensure(max(sizes) // 2)
 out = {"variant": os.environ.get("LABEL", os.environ.get("BPG_ACC_VARIANT", "0"))}
 for n in sizes:
     ctx.prof_enable(True)
-    r = bench.msm_sweep(ctx, [n], reps=8)
+    r = bench.msm_sweep(ctx, [n], reps=8, dist=os.environ.get("DIST", "uniform"))
     nl, kms, pairs = ctx.prof_read()
     ctx.prof_enable(False)
     r[str(n)]["accumulate_ms"] = kms / max(nl, 1)
