@@ -104,8 +104,18 @@ extern "C" int bpg_ctx_create(int device, bpg_ctx **out) {
     std::call_once(sizing_once, [] { if (const char *e = getenv("BPG_SIZING_MODE")) bpg_set_sizing_mode(atoi(e)); });
     bpg_ctx *ctx = new bpg_ctx();
     ctx->device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    // BPG_ACC_PRIO=0 switches the priority split off (every kernel on one default-priority stream, as in round 1)
+    static const int acc_prio = [] { const char *e2 = getenv("BPG_ACC_PRIO"); return e2 ? atoi(e2) : 1; }();
+    int prio_lo = 0, prio_hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // (numerically: lowest priority = largest value)
+    if (!acc_prio) prio_lo = prio_hi = 0;
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess && acc_prio) {
+        e = cudaStreamCreateWithPriority(&ctx->acc_stream, cudaStreamNonBlocking, prio_lo);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_acc[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_acc[1], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming);
     if (e != cudaSuccess) { // nothing of a half-built context may leak
@@ -153,6 +163,8 @@ extern "C" void bpg_ctx_destroy(bpg_ctx *ctx) {
     DSTEP("events destroyed");
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->acc_stream) cudaStreamDestroy(ctx->acc_stream);
+    for (cudaEvent_t &ev : ctx->ev_acc) if (ev) cudaEventDestroy(ev);
     DSTEP("streams destroyed");
     delete ctx;
 #undef DSTEP
@@ -364,11 +376,15 @@ static int msm_bucketize(bpg_ctx *ctx, cudaStream_t s, uint32_t nb, size_t maxpa
         digits(1, cursor, (uint32_t *)ctx->sorted.p);
         KCHECK();
         bool prof = ctx->prof_on && ctx->prof_n < 64; // the first 64 launches after bpg_prof_enable are timed
-        if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], s)); // events are pre-created by bpg_prof_enable
-        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, s>>>((const uint32_t *)ctx->sorted.p, offsets, nb, tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
+        // the accumulation runs on the context's low-priority stream (bpg_internal.h), fenced on both sides
+        cudaStream_t sa = (ctx->acc_stream && s == ctx->stream) ? ctx->acc_stream : s;
+        if (sa != s) { CUDA_TRY(cudaEventRecord(ctx->ev_acc[0], s)); CUDA_TRY(cudaStreamWaitEvent(sa, ctx->ev_acc[0], 0)); }
+        if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], sa)); // events are pre-created by bpg_prof_enable
+        k_msm_accumulate<<<LAUNCH_1D(nchunks, 128), 0, sa>>>((const uint32_t *)ctx->sorted.p, offsets, nb, tab, (ge *)ctx->buckets.p, (ge *)ctx->partial.p, CH);
         KCHECK();
+        if (prof) CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], sa));
+        if (sa != s) { CUDA_TRY(cudaEventRecord(ctx->ev_acc[1], sa)); CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_acc[1], 0)); }
         if (prof) {
-            CUDA_TRY(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], s));
             CUDA_TRY(cudaMemcpyAsync(&ctx->prof_pairs[ctx->prof_n], offsets + nb, 4, cudaMemcpyDeviceToHost, s));
             ctx->prof_n++;
         }

@@ -70,6 +70,13 @@ void prefetch_slot_free(prefetch_slot *p);
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
+    // Priority split (bpg_ctx_create): `stream` and `stream2` are created at the device's HIGHEST priority, `acc_stream` at the
+    // LOWEST, and only k_msm_accumulate is launched there (fenced by ev_acc[0] / ev_acc[1]).  With many provers sharing a GPU
+    // a multi-wave accumulate grid otherwise holds every block slot until its last wave, and the memory- / latency-bound
+    // kernels of all other proofs queue behind it; with the split the block scheduler hands freed slots to them first and
+    // they overlap with the integer-pipe-bound accumulation.
+    cudaStream_t acc_stream = nullptr;
+    cudaEvent_t ev_acc[2] = {nullptr, nullptr};
     cudaEvent_t ev = nullptr, ev2 = nullptr;
     // resident generators
     size_t cap = 0;           // per-chain capacity (power of two); tables cover 2*cap+2 points
