@@ -255,6 +255,32 @@ def msm_var_sweep(ctx, sizes, reps=3, cpu_sizes=(), cores=1):
     return out
 
 
+def fold_sweep(ctx, sizes, peak_mac):
+    """the literal IPP generator fold as a standalone op (bpg_fold_points: out_i = u^-1 P_i + u Q_i).  Kernel
+    time from the library's events around k_fold_kernel; work per output: 252 doublings + <= 142 additions of 8 field
+    multiplications each (shared-scalar Straus) = 2.27e5 MAC32."""
+    import numpy as np
+    import oracle_lib as ol
+    out = {}
+    maxn = max(sizes)
+    G, H = ctx.gens_export(0, maxn)
+    rng = np.random.default_rng(9)
+    sl = (int.from_bytes(rng.bytes(32), "little") >> 4).to_bytes(32, "little")
+    sr = (int.from_bytes(rng.bytes(32), "little") >> 4).to_bytes(32, "little")
+    mac_per_output = (252 + 142) * 8 * 72.0
+    for n in sizes:
+        ctx.fold_points(sl, sr, G[:32 * n], H[:32 * n])
+        t0 = time.perf_counter()
+        got = ctx.fold_points(sl, sr, G[:32 * n], H[:32 * n])
+        dt = time.perf_counter() - t0
+        kms = ctx.event_elapsed_ms(12, 13)
+        out[str(n)] = {"kernel_ms": kms, "outputs_per_sec_kernel": n / (kms * 1e-3), "outputs_per_sec_e2e": n / dt,
+                       "int_frac": n * mac_per_output / (kms * 1e-3) / peak_mac}
+        if n <= 4096:
+            out[str(n)]["equals_oracle"] = got == ol.fold_points(sl, sr, G[:32 * n], H[:32 * n])
+    return out
+
+
 def msm_sharded_sweep(ctx, dist, local, rank, world, sizes, reps=5, parity_n=1 << 16):
     """ONE MSM of n points split by point range over the ranks (parallel.msm_gens_sharded): every rank
     sums its slice of the resident generators, the 128-byte partial points are all-gathered over NCCL and added on every rank.
@@ -722,6 +748,7 @@ def run_ours(args):
             mim["trace" if tr else "digest"] = e
         mim["note"] = "one thread per sponge (the rounds of one sponge are sequential); int_frac against the measured dependent fe_mul chain rate"
         extras["mimc"] = mim
+        extras["fold_points"] = fold_sweep(ctx, [1 << 12] if args.quick else [1 << 12, 1 << 16, 1 << 18], peak_mac)
         sizes = [1 << k for k in range(16, 17 + 1)] if args.quick else [1 << k for k in range(16, 22 + 1)]
         if not args.quick:
             ctx.gens_ensure(1 << 21)

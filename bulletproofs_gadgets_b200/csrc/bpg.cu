@@ -844,8 +844,11 @@ extern "C" int bpg_fold_points(bpg_ctx *ctx, const uint8_t sl[32], const uint8_t
     CUDA_TRY(cudaMemcpyAsync(d_ok, &one, 4, cudaMemcpyHostToDevice, s));
     k_decompress_kernel<<<LAUNCH_1D(2 * n, 128), 0, s>>>(d + 64, (uint32_t)(2 * n), pts, d_ok);
     KCHECK();
+    for (int e = 12; e < 14; e++) if (!ctx->tev[e]) CUDA_TRY(cudaEventCreate(&ctx->tev[e]));
+    CUDA_TRY(cudaEventRecord(ctx->tev[12], s)); // event slots 12 / 13 bracket the fold kernel (bpg_event_elapsed_ms)
     k_fold_kernel<<<LAUNCH_1D(n, 64), 0, s>>>((const sc *)d, (const sc *)(d + 32), pts, pts + n, (uint32_t)n, pts + 2 * n);
     KCHECK();
+    CUDA_TRY(cudaEventRecord(ctx->tev[13], s));
     CTX_TRY(run_compress(ctx, s, pts + 2 * n, n, d + 64));
     D2H_TRY(ctx, out32, d + 64, 32 * n, s);
     D2H_TRY(ctx, &ok, d_ok, 4, s);

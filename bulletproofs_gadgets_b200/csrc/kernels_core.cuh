@@ -321,20 +321,55 @@ __global__ void __launch_bounds__(64) k_points_sum_kernel(const ge *__restrict__
     block_sum_points(acc, smem);
     if (threadIdx.x == 0) st_ge(&block_out[blockIdx.x], acc);
 }
-// IPP generator fold as a standalone op: out[i] = sl*PL[i] + sr*PR[i]
+// IPP generator fold as a standalone op (K5; the literal per-round fold of dalek's InnerProductProof::create, off the proving
+// hot path here -- see DESIGN.md "late fold"): out[i] = sl * PL[i] + sr * PR[i], the SAME two scalars for every output.
+// Shared-scalar Straus: the signed radix-16 digits of sl and sr are recoded once per block into shared memory, every thread
+// builds the 8 multiples of its two points and walks ONE doubling chain (252 doublings + <= 128 table additions instead of two
+// chains); the digit pattern is identical for all threads, so the sign / zero branches never diverge.
 __global__ void __launch_bounds__(64) k_fold_kernel(const sc *__restrict__ sl, const sc *__restrict__ sr, const ge *__restrict__ PL, const ge *__restrict__ PR,
                                                      uint32_t n, ge *__restrict__ out) {
+    __shared__ signed char dg[2][64];
+    if (threadIdx.x < 2) {
+        sc k;
+        ld_sc(k, threadIdx.x ? sr : sl);
+        sc_reduce(k, k);
+        int carry = 0;
+        for (int i = 0; i < 64; i++) {
+            int b = (int)((k.v[i >> 3] >> (4 * (i & 7))) & 0xF) + carry;
+            carry = b >= 8;
+            dg[threadIdx.x][i] = (signed char)(b - (carry << 4)); // k < 2^253: the top digit never carries out
+        }
+    }
+    __syncthreads();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    sc a, b;
-    ld_sc(a, sl); ld_sc(b, sr);
-    sc_reduce(a, a); sc_reduce(b, b);
-    ge p, q, r1, r2;
-    ld_ge(p, &PL[i]); ld_ge(q, &PR[i]);
-    ge_scalarmul_w4(r1, a, p);
-    ge_scalarmul_w4(r2, b, q);
-    ge_add(r1, r1, r2);
-    st_ge(&out[i], r1);
+    ge_pn tl[8], tr[8];
+    {
+        ge cur;
+        ld_ge(cur, &PL[i]);
+        ge_to_pn(tl[0], cur);
+#pragma unroll 1
+        for (int j = 1; j < 8; j++) { ge_add_pn(cur, cur, tl[0]); ge_to_pn(tl[j], cur); }
+        ld_ge(cur, &PR[i]);
+        ge_to_pn(tr[0], cur);
+#pragma unroll 1
+        for (int j = 1; j < 8; j++) { ge_add_pn(cur, cur, tr[0]); ge_to_pn(tr[j], cur); }
+    }
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) { ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); }
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            int d = dg[side][w];
+            if (d == 0) continue;
+            ge_pn e = side ? tr[(d < 0 ? -d : d) - 1] : tl[(d < 0 ? -d : d) - 1];
+            if (d < 0) { ge_pn m; ge_pn_neg(m, e); e = m; }
+            ge_add_pn(acc, acc, e);
+        }
+    }
+    st_ge(&out[i], acc);
 }
 
 // ---------------------------------------------------------------- integer-pipe microbenchmark

@@ -212,7 +212,7 @@ int bpg_host_alloc(bpg_ctx *ctx, size_t bytes, void **h_ptr);
 int bpg_host_free(bpg_ctx *ctx, void *h_ptr);
 
 /* timing on the library's own stream: record event slot i (0..15), elapsed milliseconds between two slots
- * (slots 14 / 15 are recorded by bpg_mimc_sponge_batch around its kernel) */
+ * (slots 14 / 15 are recorded by bpg_mimc_sponge_batch around its kernel, 12 / 13 by bpg_fold_points around the fold kernel) */
 int bpg_event_record(bpg_ctx *ctx, int slot);
 int bpg_event_elapsed_ms(bpg_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* per-kernel profile of the MSM bucket-accumulation kernel (the dominant kernel): while enabled every launch is

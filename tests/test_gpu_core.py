@@ -110,6 +110,19 @@ def test_variable_base_msm_and_fold(ctx):
     assert out == ol.fold_points(pr.sc_bytes(ui), pr.sc_bytes(u), G[:32 * 64], G[32 * 64:32 * 128])
 
 
+def test_fold_points_shared_scalar_straus_edges(ctx):
+    """the literal IPP generator fold G'_i = u^-1 G_i + u G_{i+h} (dalek InnerProductProof::create, behind prover.rs:93): ragged
+    sizes around the 64-thread block, scalars 0, 1, l - 1, unreduced 2^255 - 1, digits that carry into every window"""
+    rnd = random.Random(61)
+    G, H = ol.gens(0, 331)
+    for n in (1, 63, 64, 65, 331):
+        for sl, sr in ((0, 0), (1, 0), (0, 1), (L - 1, 1), (2 ** 255 - 1, 2 ** 255 - 1), (int("8" * 63, 16) % L, int("f" * 63, 16) % L),
+                       (rnd.randrange(L), rnd.randrange(L))):
+            a, b = sl.to_bytes(32, "little"), sr.to_bytes(32, "little")  # the device reduces mod l itself (a12: Scalar semantics)
+            want = ol.fold_points(pr.sc_bytes(sl % L), pr.sc_bytes(sr % L), G[:32 * n], H[:32 * n])
+            assert ctx.fold_points(a, b, G[:32 * n], H[:32 * n]) == want, (n, sl, sr)
+
+
 def test_device_resident_and_partial_sum(ctx):
     rnd = random.Random(7)
     n = 512
