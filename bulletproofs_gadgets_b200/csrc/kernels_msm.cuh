@@ -292,7 +292,10 @@ __device__ __forceinline__ void msm_load_entry(ge_an &a, const ge_an *__restrict
 // partial slot layout: partial[2*chunk + 0] = run touching the chunk start, [2*chunk + 1] = run touching the chunk end only
 // (Tried and dropped, profiles/r02_accumulate_variants.jsonl: prefetch.global.L1 / .L2 of the next pair's entry one iteration
 // ahead -- 12.9 -> 9.6 G additions/s; entries padded to one aligned 128-byte line -- DRAM traffic down, time unchanged.)
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets, uint32_t nbuckets,
+#ifndef BPG_ACC_MINBLOCKS
+#define BPG_ACC_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, BPG_ACC_MINBLOCKS) k_msm_accumulate(const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets, uint32_t nbuckets,
                                                          const ge_an *__restrict__ tab, ge *__restrict__ buckets, ge *__restrict__ partial, uint32_t CH) {
     uint32_t M = offsets[nbuckets];
     uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
