@@ -291,7 +291,9 @@ __device__ __forceinline__ void msm_load_entry(ge_an &a, const ge_an *__restrict
 
 // partial slot layout: partial[2*chunk + 0] = run touching the chunk start, [2*chunk + 1] = run touching the chunk end only
 // (Tried and dropped, profiles/r02_accumulate_variants.jsonl: prefetch.global.L1 / .L2 of the next pair's entry one iteration
-// ahead -- 12.9 -> 9.6 G additions/s; entries padded to one aligned 128-byte line -- DRAM traffic down, time unchanged.)
+// ahead -- 12.9 -> 9.6 G additions/s; entries padded to one aligned 128-byte line -- DRAM traffic down, time unchanged;
+// 5 / 6 resident blocks per SM (96 / 80 registers) -- neutral / slower; requesting the next entry between the two multiplication
+// stages keeps it live through stage 2: 134 registers, and ptxas sinks the loads to the end of the body anyway.)
 #ifndef BPG_ACC_MINBLOCKS
 #define BPG_ACC_MINBLOCKS 1
 #endif
