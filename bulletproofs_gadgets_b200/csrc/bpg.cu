@@ -647,7 +647,7 @@ int msm_materialise_fold(bpg_ctx *ctx, cudaStream_t s, uint32_t N, uint32_t npri
     if (sharded) CTX_TRY(shard_exchange_sum(ctx, s, (ge *)ctx->mat_pts.p, nout));
     k_mat_chain<<<LAUNCH_1D(nout, 64), 0, s>>>((const ge *)ctx->mat_pts.p, nout, (ge *)ctx->mat_ext.p);
     KCHECK();
-    k_mat_affine<<<LAUNCH_1D(BPG_NWIN * nout + BPG_NWIN, 64), 0, s>>>((const ge *)ctx->mat_ext.p, nout, pt_small, (ge_an *)ctx->mat_tab.p, ctx->tab, ptotal,
+    k_mat_affine<<<LAUNCH_1D(nout + BPG_NWIN, 64), 0, s>>>((const ge *)ctx->mat_ext.p, nout, pt_small, (ge_an *)ctx->mat_tab.p, ctx->tab, ptotal,
                                                                       2 * cap);
     KCHECK();
     return BPG_OK;

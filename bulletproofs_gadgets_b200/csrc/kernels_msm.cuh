@@ -721,21 +721,39 @@ __global__ void __launch_bounds__(64) k_mat_chain(const ge *__restrict__ pts, ui
         }
     }
 }
-// affine-Niels table of the materialised points (one thread per (window, point): its own inversion), plus the entries of
-// one resident point (B) copied from the main table to index npts
+// affine-Niels table of the materialised points, plus the entries of one resident point (B) copied from the main table to
+// index npts.  One thread per POINT: the 16 window multiples of a point share ONE field inversion (Montgomery's trick over
+// their Z coordinates: 45 multiplications instead of 15 more inversions of ~265 each; round 1 inverted per entry -- 0.62 ms of
+// integer-pipe work per 2^20 proof).
 __global__ void __launch_bounds__(64) k_mat_affine(const ge *__restrict__ ext, uint32_t npts, uint32_t ptotal_small, ge_an *__restrict__ tab_small,
                                                     const ge_an *__restrict__ tab_main, uint32_t ptotal_main, uint32_t pB_main) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = BPG_NWIN * npts;
-    if (t < total) {
-        uint32_t w = t / npts, q = t - w * npts;
-        ge p;
-        ld_ge(p, &ext[t]);
-        ge_an a;
-        ge_to_an(a, p);
-        st_an(&tab_small[(size_t)w * ptotal_small + q], a);
-    } else if (t < total + BPG_NWIN) {
-        uint32_t w = t - total;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < npts) {
+        fe pre[BPG_NWIN]; // pre[w] = Z_0 Z_1 ... Z_w
+        ld_fe_nc(pre[0], &ext[q].Z);
+#pragma unroll 1
+        for (int w = 1; w < BPG_NWIN; w++) {
+            fe z;
+            ld_fe_nc(z, &ext[(size_t)w * npts + q].Z);
+            fe_mul(pre[w], pre[w - 1], z);
+        }
+        fe inv;
+        fe_invert(inv, pre[BPG_NWIN - 1]);
+#pragma unroll 1
+        for (int w = BPG_NWIN - 1; w >= 0; w--) {
+            ge p;
+            ld_ge(p, &ext[(size_t)w * npts + q]);
+            fe zi;
+            if (w) { fe_mul(zi, inv, pre[w - 1]); fe_mul(inv, inv, p.Z); } else zi = inv;
+            fe x, y;
+            fe_mul(x, p.X, zi);
+            fe_mul(y, p.Y, zi);
+            ge_an a;
+            ge_affine_to_an(a, x, y);
+            st_an(&tab_small[(size_t)w * ptotal_small + q], a);
+        }
+    } else if (q < npts + BPG_NWIN) {
+        uint32_t w = q - npts;
         ge_an a;
         ld_an(a, &tab_main[(size_t)w * ptotal_main + pB_main]);
         st_an(&tab_small[(size_t)w * ptotal_small + npts], a);
