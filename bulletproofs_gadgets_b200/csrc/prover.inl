@@ -159,8 +159,8 @@ extern "C" int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t
     std::vector<uint32_t> level(n, 0);
     uint32_t depth = 0;
     for (size_t i = 0; i < n; i++) {
-        uint32_t t0 = lc_ptr[2 * i], t1 = lc_ptr[2 * i + 2];
-        if (t1 < t0 || t1 > T) return BPG_E_ARG;
+        uint32_t t0 = lc_ptr[2 * i], tm = lc_ptr[2 * i + 1], t1 = lc_ptr[2 * i + 2];
+        if (tm < t0 || t1 < tm || t1 > T) return BPG_E_ARG; // the two term ranges of a multiplier must be nested in [0, T]
         if (t0 == t1) continue;
         uint32_t lv = 1;
         for (uint32_t t = t0; t < t1; t++) {

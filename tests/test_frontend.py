@@ -152,6 +152,8 @@ def test_device_witness_evaluation_edge_cases():
     tv = (C.c_uint32 * 2)((0 << 29) | 2, 4 << 29)  # multiplier 1 references a_L[2]
     bufs = [C.create_string_buffer(32 * n) for _ in range(3)]
     assert ctx.lib.bpg_witness_eval(ctx.h, n, 0, ptr, tv, bytes(64), None, *bufs) == -4  # BPG_E_ARG
+    bad = (C.c_uint32 * (2 * n + 1))(0, 0, 0, 2, 1, 2, 2)  # a middle pointer outside its multiplier's range
+    assert ctx.lib.bpg_witness_eval(ctx.h, n, 0, bad, (C.c_uint32 * 2)(4 << 29, 4 << 29), bytes(64), None, *bufs) == -4
 
 
 @pytest.mark.gpu
