@@ -443,6 +443,17 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
     // large single-group MSMs: shared-memory privatised histogram / scatter (one block per SM), see kernels_msm.cuh
     bool priv = (!vb && G <= BPG_MAX_GROUPS && total >= BPG_PRIV_MSM_TERMS);
     int sms = 0;
+    // upper bound of the terms any one group receives (a segment whose group alternates by halves gives each of the two half)
+    uint32_t max_group_terms = 0;
+    {
+        uint32_t per[2 * BPG_MAX_GROUPS] = {0};
+        for (int i = 0; i < plan->nseg && G <= BPG_MAX_GROUPS; i++) {
+            const msm_seg &sg = plan->seg[i];
+            if (sg.alt) { per[sg.group] += (sg.n + 1) / 2 + 1; per[sg.group ^ 1u] += (sg.n + 1) / 2 + 1; }
+            else per[sg.group] += sg.n;
+        }
+        for (uint32_t v : per) max_group_terms = std::max(max_group_terms, v);
+    }
     if (priv) {
         // (idempotent and cheap; setting it per call keeps it correct for every device without shared mutable state)
         CUDA_TRY(cudaFuncSetAttribute(k_msm_hist_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPG_NBP * 4)));
@@ -455,7 +466,12 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
             // the 126 MB L2 and the plain cursor-ordered scatter (33 K open sectors) is faster again
             // (measured 2^19 / 2^20 / 2^21 / 2^22 terms: 1.14 / 1.90 / 3.85 / 8.11 ms privatised vs 1.18 / 1.99 / 3.60 / 6.89 ms plain)
             const bool priv_scatter = total <= (1u << 20);
-            if (scatter && priv_scatter) k_msm_scatter_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc, sorted);
+            // several groups of at most 2^20 terms each (the L / R pair of an IPP round over 2 x 2^20 generators, A_I / A_O):
+            // one privatised launch per group, one after the other (BPG_SCATTER_PG=0 switches this off for A/B runs)
+            static const int scatter_pg = [] { const char *e = getenv("BPG_SCATTER_PG"); return e ? atoi(e) : 1; }();
+            const bool per_group = scatter_pg && !priv_scatter && G > 1 && max_group_terms <= (1u << 20) + 64;
+            if (scatter && per_group) { for (int g = 0; g < G; g++) k_msm_scatter_smem<<<dim3(sms, 1), 1024, BPG_NBP * 4, s>>>(P, cc, sorted, (uint32_t)g); }
+            else if (scatter && priv_scatter) k_msm_scatter_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc, sorted, 0u);
             else if (scatter) k_msm_digits<1, 0><<<LAUNCH_1D(total, 256), 0, s>>>(P, cc, sorted);
             else k_msm_hist_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc);
         } else {

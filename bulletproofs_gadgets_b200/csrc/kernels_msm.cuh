@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(1024, 1) k_msm_hist_smem(msm_params P, uint32_
         if (c) atomicAdd(&cg[i], c);
     }
 }
-__global__ void __launch_bounds__(1024, 1) k_msm_scatter_smem(msm_params P, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+// (g0: first group of this launch -- msm_run_local launches the groups of a multi-group MSM one after the other when each of
+// them is within the privatised scatter's reach, so that only ONE group's open ranges compete for L2 at a time)
+__global__ void __launch_bounds__(1024, 1) k_msm_scatter_smem(msm_params P, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted, uint32_t g0) {
     extern __shared__ uint32_t scnt[];
-    const uint32_t g = blockIdx.y;
+    const uint32_t g = g0 + blockIdx.y;
     for (uint32_t i = threadIdx.x; i < BPG_NBP; i += blockDim.x) scnt[i] = 0;
     __syncthreads();
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += gridDim.x * blockDim.x) {

@@ -258,3 +258,27 @@ def test_prefetched_opening_gives_identical_proofs(ctx):
     prefetch(exts[0], blinds=inst["blinds"][32:] + inst["blinds"][:32])  # hint for other blindings: must not be used
     assert prove(exts[0]) == want[0]
     ctx.lib.bpg_circuit_destroy(h)
+
+
+def test_page_locked_host_buffers_give_identical_proofs(ctx):
+    """bpg_host_alloc: a witness handed over in page-locked host memory (one asynchronous DMA) must give the proof bytes of the
+    same witness in ordinary memory, which equal the oracle's; freeing and re-allocating leaves the library usable"""
+    import circuits
+    from bulletproofs_gadgets_b200 import gadgets
+    inst = circuits.chain_instance(500, 91)
+    rp, tv, tc = inst["csr"]
+    import numpy as np
+    circ = gadgets.Circuit(ctx, inst["n"], 3, (np.array(rp, dtype=np.uint32), np.array(tv, dtype=np.uint32), tc))
+    ext = b"\x5a" * 32
+    want = circ.prove(inst, ext)
+    assert want == oracle_prove(inst, 4096, ext)
+    for _ in range(2):
+        pinned, handles = dict(inst), []
+        for k in ("aL", "aR", "aO"):
+            ptr, hnd = ctx.host_alloc(inst[k])
+            pinned[k] = ptr
+            handles.append(hnd)
+        assert circ.prove(pinned, ext) == want
+        for hnd in handles:
+            ctx.host_free(hnd)
+    circ.close()
