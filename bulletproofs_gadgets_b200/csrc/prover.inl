@@ -452,26 +452,11 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         msm_seg &sg = plan.seg[plan.nseg++];
         sg.scalars = sp; sg.n = (uint32_t)cnt; sg.p0 = p0; sg.group = g; sg.reduce = 0;
     };
-    // Large circuits: <a_L, G> and <a_R, H> (and below <s_L, G>, <s_R, H>) are evaluated as output groups of their own and added
-    // afterwards.  A group of at most 2^20 terms is within the reach of the privatised scatter (its part of the sorted array
-    // stays in L2), a single group of 2n terms is not: 0.73 -> 2 x 0.18 ms per commitment MSM at n = 2^20.
-    const bool split_commit = 2 * n + 1 > ((size_t)1 << 20) && n + 1 <= ((size_t)1 << 20) + 64;
-    ge *res_parts = res + 5; // three spare slots behind the compressed-output area
-    if (split_commit) {
-        plan.ngroups = 3;
-        add_seg(d_aL, n, 0, 0); add_seg(d_small + 0, 1, pBb, 0);
-        add_seg(d_aR, n, (uint32_t)ctx->cap, 1);
-        add_seg(d_aO, n, 0, 2); add_seg(d_small + 1, 1, pBb, 2);
-        CTX_TRY(msm_run(ctx, s, &plan, res_parts));
-        k_points_sum_kernel<<<1, 64, 0, s>>>(res_parts, 2, res);         // A_I = <a_L, G> + ib B~ + <a_R, H>
-        KCHECK();
-        k_points_sum_kernel<<<1, 64, 0, s>>>(res_parts + 2, 1, res + 1); // A_O
-        KCHECK();
-    } else {
-        add_seg(d_aL, n, 0, 0); add_seg(d_aR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 0, 1, pBb, 0);
-        add_seg(d_aO, n, 0, 1); add_seg(d_small + 1, 1, pBb, 1);
-        CTX_TRY(msm_run(ctx, s, &plan, res));
-    }
+    // (Evaluating <a_L, G> and <a_R, H> as output groups of their own -- each then within the privatised scatter's reach -- was
+    // measured: 58.0 -> 57.8 ms per 2^20 proof, not worth a third bucket set; profiles/r02_sort_variants.jsonl.)
+    add_seg(d_aL, n, 0, 0); add_seg(d_aR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 0, 1, pBb, 0);
+    add_seg(d_aO, n, 0, 1); add_seg(d_small + 1, 1, pBb, 1);
+    CTX_TRY(msm_run(ctx, s, &plan, res));
     tr.mark("launchAIAO");
     // s_L, s_R: 2n sequential TranscriptRng draws on the host (byte-exact with the reference) ...
     if (flags & BPG_FLAG_FAST_BLINDING) {
@@ -530,18 +515,9 @@ extern "C" long bpg_r1cs_prove(bpg_ctx *ctx, bpg_circuit *c, const uint8_t *labe
         }
     }
     memset(&plan, 0, sizeof plan); plan.lean = bpg_lean_now(); plan.shard = shard_on;
-    if (split_commit) {
-        plan.ngroups = 2;
-        add_seg(d_sL, n, 0, 0); add_seg(d_small + 2, 1, pBb, 0);
-        add_seg(d_sR, n, (uint32_t)ctx->cap, 1);
-        CTX_TRY(msm_run(ctx, s, &plan, res_parts));
-        k_points_sum_kernel<<<1, 64, 0, s>>>(res_parts, 2, res + 2);
-        KCHECK();
-    } else {
-        plan.ngroups = 1;
-        add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
-        CTX_TRY(msm_run(ctx, s, &plan, res + 2));
-    }
+    plan.ngroups = 1;
+    add_seg(d_sL, n, 0, 0); add_seg(d_sR, n, (uint32_t)ctx->cap, 0); add_seg(d_small + 2, 1, pBb, 0);
+    CTX_TRY(msm_run(ctx, s, &plan, res + 2));
     CTX_TRY(run_compress(ctx, s, res, 3, d_enc));
     uint8_t AIe[32], AOe[32], Se[32], h_enc[96];
     D2H_TRY(ctx, h_enc, d_enc, 96, s);
