@@ -49,6 +49,13 @@ def main():
                      "gens_tables_ms": t_g, "circuit_upload_ms": t_c, "prove_ms_byte_exact": t_exact, "prove_ms_fast_blinding": t_fast,
                      "verify_ms": t_ver, "proof_bytes": len(proof), "verifier_accepts": bool(ok and ok_f), "tamper_rejected": rej}
         circ.close()
+        if os.environ.get("BPG_CONFIGS_CPU", "1") == "1":
+            # the CPU oracle beside it (all host cores; test infrastructure, timed as the baseline only)
+            import bench
+            cores = os.cpu_count() or 1
+            bench.oracle_prove(inst, cap, ext, cores)  # first call derives the generators
+            t_cpu, proof_cpu, V_cpu = bench.oracle_prove(inst, cap, ext, cores)
+            res[name].update({"cpu_prove_ms": 1e3 * t_cpu, "cpu_cores": cores, "proof_bytes_equal_oracle": (proof_cpu, V_cpu) == (proof, V)})
 
     if "0" in which:
         # config 0: the reference's own example.gadgets/.inst/.wtns through the front-end driver (prover + verifier binaries)
@@ -67,6 +74,17 @@ def main():
         t_dev, _ = timed(lambda: prun.prover.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32)), 2)
         res["config0_example_cli"] = {"constraints": nc, "multipliers": prun.prover.get_num_multiplications(), "prover_cli_ms_incl_python_frontend": t_p,
                                       "verifier_cli_ms_incl_python_frontend": t_v, "prove_call_ms": t_dev, "verifier_prints": "true" if ok else "false"}
+        if os.environ.get("BPG_CONFIGS_CPU", "1") == "1":
+            import oracle_lib as ol
+            p = prun.prover
+            rp, tv, tc = p.csr()
+            enc = lambda xs: b"".join(int(x).to_bytes(32, "little") for x in xs)
+            aL, aR, aO = p.witness_bytes()
+            ol.lib().bpo_set_threads(os.cpu_count() or 1)
+            ol.gens(0, 1 << 14)
+            t_cpu, (proof_cpu, _) = timed(lambda: ol.r1cs_prove(b"example", 1 << 14, aL, aR, aO, enc(p.v), enc(p.v_blinding), rp, tv, tc, bytes(32)), 2)
+            proof_gpu, _ = p.prove(bpg.BulletproofGens.new(1 << 14, 1, ctx=ctx), ext_rng32=bytes(32))
+            res["config0_example_cli"].update({"cpu_prove_ms": t_cpu, "cpu_cores": os.cpu_count(), "proof_bytes_equal_oracle": proof_cpu == proof_gpu})
     if "3" in which:
         t0 = time.perf_counter()
         inst = gadgets.bounds_check_batch_instance(4096, 8, seed=5)
