@@ -177,18 +177,19 @@ extern "C" int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t
     for (uint32_t l = 0; l <= depth; l++) lptr[l + 1] += lptr[l];
     { std::vector<uint32_t> pos(lptr.begin(), lptr.end() - 1); for (size_t i = 0; i < n; i++) order[pos[level[i]]++] = (uint32_t)i; }
     cudaStream_t s = ctx->stream;
-    size_t b_w = 3 * 32 * n, b_v = 32 * m, b_ord = 4 * n, b_ptr = 4 * (2 * n + 1), b_tv = 4 * T, b_tc = 32 * T;
+    size_t b_w = 3 * 32 * n, b_v = 32 * m, b_ord = 4 * n, b_ptr = 4 * (2 * n + 1), b_tv = 4 * T, b_tc = 32 * T, b_lp = 4 * ((size_t)depth + 2);
     CTX_TRY(ctx->scratch[8].ensure(b_w + b_v + 64));
-    CTX_TRY(ctx->scratch[11].ensure(b_ord + b_ptr + b_tv + b_tc + 256));
+    CTX_TRY(ctx->scratch[11].ensure(b_ord + b_ptr + b_tv + b_tc + b_lp + 256));
     sc *d_aL = (sc *)ctx->scratch[8].p, *d_aR = d_aL + n, *d_aO = d_aR + n, *d_v = d_aO + n;
     uint8_t *d = (uint8_t *)ctx->scratch[11].p;
     sc *d_tc = (sc *)d;                                  // 32-byte aligned first
-    uint32_t *d_order = (uint32_t *)(d + b_tc), *d_ptr = d_order + n, *d_tv = d_ptr + (2 * n + 1);
+    uint32_t *d_order = (uint32_t *)(d + b_tc), *d_ptr = d_order + n, *d_tv = d_ptr + (2 * n + 1), *d_lptr = d_tv + T;
     CUDA_TRY(cudaMemcpyAsync(d_aL, aL, 32 * n, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_aR, aR, 32 * n, cudaMemcpyHostToDevice, s));
     if (m) CUDA_TRY(cudaMemcpyAsync(d_v, v, b_v, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), b_ord, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_ptr, lc_ptr, b_ptr, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_lptr, lptr.data(), b_lp, cudaMemcpyHostToDevice, s));
     if (T) {
         CUDA_TRY(cudaMemcpyAsync(d_tv, term_var, b_tv, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(d_tc, term_coeff, b_tc, cudaMemcpyHostToDevice, s));
@@ -199,11 +200,21 @@ extern "C" int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t
     KCHECK();
     if (m) { k_sc_reduce_inplace<<<LAUNCH_1D(m, 256), 0, s>>>(d_v, (uint32_t)m); KCHECK(); }
     if (lptr[1]) { k_witness_assigned<<<LAUNCH_1D(lptr[1], 128), 0, s>>>(d_order, lptr[1], d_aL, d_aR, d_aO); KCHECK(); }
-    for (uint32_t l = 1; l <= depth; l++) {
+    // wide levels: one grid each; runs of consecutive narrow levels (<= 256 multipliers): one single-block launch per run
+    const uint32_t NARROW = 256;
+    for (uint32_t l = 1; l <= depth;) {
         uint32_t k0 = lptr[l], k1 = lptr[l + 1];
-        if (k1 == k0) continue;
-        k_witness_level<<<LAUNCH_1D(k1 - k0, 128), 0, s>>>(d_order, k0, k1, d_ptr, d_tv, d_tc, d_aL, d_aR, d_aO, d_v);
+        if (k1 - k0 > NARROW) {
+            k_witness_level<<<LAUNCH_1D(k1 - k0, 128), 0, s>>>(d_order, k0, k1, d_ptr, d_tv, d_tc, d_aL, d_aR, d_aO, d_v);
+            KCHECK();
+            l++;
+            continue;
+        }
+        uint32_t l1 = l + 1;
+        while (l1 <= depth && lptr[l1 + 1] - lptr[l1] <= NARROW) l1++;
+        k_witness_levels_block<<<1, 256, 0, s>>>(d_order, d_lptr, l, l1, d_ptr, d_tv, d_tc, d_aL, d_aR, d_aO, d_v);
         KCHECK();
+        l = l1;
     }
     D2H_TRY(ctx, aL, d_aL, 32 * n, s);
     D2H_TRY(ctx, aR, d_aR, 32 * n, s);

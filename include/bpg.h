@@ -148,7 +148,8 @@ void bpg_circuit_destroy(bpg_circuit *c);
  * left_1, ... inside term_var / term_coeff (encoding as for bpg_circuit_create); a term may reference committed values (v, m of
  * them), One, and multipliers with a SMALLER index only.  Multipliers made by allocate_multiplier / allocate have an empty pair
  * of combinations: their a_L, a_R are inputs (aL, aR are in/out, n x 32 bytes), a_O is computed.  The dependency graph is
- * levelised on the host and every level is one launch (independent multipliers in parallel). */
+ * levelised on the host; a wide level is one launch (independent multipliers in parallel), a run of narrow levels one
+ * single-block launch. */
 int bpg_witness_eval(bpg_ctx *ctx, size_t n, size_t m, const uint32_t *lc_ptr, const uint32_t *term_var, const uint8_t *term_coeff,
                      const uint8_t *v, uint8_t *aL, uint8_t *aR, uint8_t *aO);
 
