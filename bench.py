@@ -843,7 +843,8 @@ def run_ours(args):
                              "share_of_step": (sum(m for m, _ in per_launch) / solo_ms) if solo_ms > 0 else None,
                              "share_note": "all k_msm_accumulate launches / device time of the same solo proof (compare profiles/r02_launch_summary_2p20.txt)",
                              "in_timed_region": {"launches": int(nl_c), "avg_launch_ms": kms_c / nl_c if nl_c else None,
-                                                 "note": "lane 0's launches while %d other provers share the GPU" % (P - 1)}},
+                                                 "note": "lane 0's launches while %d other provers share the GPU: the kernel runs on a lowest-priority stream, so this "
+                                                         "interval includes the time its blocks wait for slots behind every other prover's kernels" % (P - 1)}},
                 "cpu_baseline": cpu, "clocks": sampler.summary()}
         line.update(extras)
         _emit(json.dumps(line))
