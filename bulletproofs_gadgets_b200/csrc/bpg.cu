@@ -469,6 +469,9 @@ static int msm_run_local(bpg_ctx *ctx, cudaStream_t s, msm_plan *plan, ge *d_out
             // several groups of at most 2^20 terms each (the L / R pair of an IPP round over 2 x 2^20 generators, A_I / A_O):
             // one privatised launch per group, one after the other (BPG_SCATTER_PG=0 switches this off for A/B runs)
             static const int scatter_pg = [] { const char *e = getenv("BPG_SCATTER_PG"); return e ? atoi(e) : 1; }();
+            // (block size of the privatised kernels, profiles/r02_sort_variants.jsonl: 1024 / 512 / 256 threads -> 57.8 / 59.5 / 60.4 ms per
+            // solo 2^20 proof, 24.3 / 24.4 proofs/s with 48 provers: smaller blocks leave more registers to co-resident accumulate
+            // blocks but are slower themselves)
             const bool per_group = scatter_pg && !priv_scatter && G > 1 && max_group_terms <= (1u << 20) + 64;
             if (scatter && per_group) { for (int g = 0; g < G; g++) k_msm_scatter_smem<<<dim3(sms, 1), 1024, BPG_NBP * 4, s>>>(P, cc, sorted, (uint32_t)g); }
             else if (scatter && priv_scatter) k_msm_scatter_smem<<<dim3(sms, G), 1024, BPG_NBP * 4, s>>>(P, cc, sorted, 0u);
