@@ -125,8 +125,10 @@ public:
         int waits = 0;
         while (!job.done) {
             // lead if nobody does, or if the current leaders have had no free lane for this stream for a whole slice
-            if (!job.adopted && (leaders == 0 || waits >= 4)) { lead(lk, &job); continue; }
-            cv.wait_for(lk, std::chrono::microseconds(500));
+            // (the timed wait is only a safety net for the hand-over -- finished streams and retiring leaders notify; with
+            // hundreds of waiting prover threads on a 32-core host a 0.5 ms poll cost about two cores)
+            if (!job.adopted && (leaders == 0 || waits >= 2)) { lead(lk, &job); continue; }
+            cv.wait_for(lk, std::chrono::microseconds(1000));
             waits++;
         }
         memcpy(s.st, job.st, sizeof job.st); // position and flags are those of the steady state again
